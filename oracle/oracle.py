@@ -1,0 +1,194 @@
+"""ctypes loader for oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product package (scir_b200/) never does.
+Every wrapper names the reference lines the C function restates (see fir_oracle.c).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc, -ffp-contract=off)."""
+    src = os.path.join(_HERE, "fir_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _SO
+
+
+class ResamplePlan(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "up", "down", "n_out", "half_len", "n_pre_pad", "n_post_pad", "n_pre_remove",
+        "len_h_padded", "upfirdn_len")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.oracle_upfirdn_out_len.restype = C.c_int64
+        _lib.oracle_upfirdn_out_len.argtypes = [C.c_int64] * 4
+        _lib.oracle_legacy_resample_poly_2_3.restype = C.c_int64
+        _lib.oracle_fir1d_batched_f32_mt.restype = C.c_int
+        _lib.oracle_filtfilt_fir_f32.restype = C.c_int
+        _lib.oracle_version.restype = C.c_char_p
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(v):
+    return C.c_int64(int(v))
+
+
+def fir1d_batched_f32(x, taps):
+    """Reference f32 loop, reference tap order (gpu/lib.rs:1134-1152)."""
+    x = _f32(x); taps = _f32(taps)
+    assert x.ndim == 2 and taps.ndim == 1
+    y = np.empty_like(x)
+    lib().oracle_fir1d_batched_f32(_p(x), _i64(x.shape[0]), _i64(x.shape[1]), _p(taps),
+                                   _i64(taps.size), _p(y))
+    return y
+
+
+def fir1d_batched_f32_mt(x, taps, threads):
+    """Row-parallel version of the same loop; returns (y, threads_used)."""
+    x = _f32(x); taps = _f32(taps)
+    y = np.empty_like(x)
+    used = lib().oracle_fir1d_batched_f32_mt(_p(x), _i64(x.shape[0]), _i64(x.shape[1]),
+                                             _p(taps), _i64(taps.size), _p(y), C.c_int(threads))
+    return y, int(used)
+
+
+def fir1d_batched_f64(x, taps):
+    """Reference f64 loop (gpu/lib.rs:1166-1184)."""
+    x = _f64(x); taps = _f64(taps)
+    y = np.empty_like(x)
+    lib().oracle_fir1d_batched_f64(_p(x), _i64(x.shape[0]), _i64(x.shape[1]), _p(taps),
+                                   _i64(taps.size), _p(y))
+    return y
+
+
+def fir1d_batched_f32_acc64(x, taps):
+    """f32 data/taps, f64 products and sums: the judge for the 1e-5 tolerance."""
+    x = _f32(x); taps = _f32(taps)
+    y = np.empty(x.shape, dtype=np.float64)
+    lib().oracle_fir1d_batched_f32_acc64(_p(x), _i64(x.shape[0]), _i64(x.shape[1]), _p(taps),
+                                         _i64(taps.size), _p(y))
+    return y
+
+
+def legacy_resample_taps():
+    """31 taps of the reference's 2/3 resampler, regenerated (sig/lib.rs:315-347)."""
+    h = np.empty(31, dtype=np.float64)
+    lib().oracle_legacy_resample_taps(_p(h))
+    return h
+
+
+def legacy_resample_poly_2_3(x, h=None):
+    """scir_signal::resample_poly(x, 2, 3) (sig/lib.rs:313-362), f64."""
+    x = _f64(x)
+    h = legacy_resample_taps() if h is None else _f64(h)
+    y = np.empty((2 * x.size) // 3 + 2, dtype=np.float64)
+    cnt = lib().oracle_legacy_resample_poly_2_3(_p(x), _i64(x.size), _p(h), _p(y))
+    return y[:cnt].copy()
+
+
+def filtfilt_fir_nopad(b, x):
+    """Reference-structure forward-backward (sig/lib.rs:278-291) with an FIR b; f64 sums."""
+    b = _f32(b); x = _f32(x)
+    y = np.empty(x.shape, dtype=np.float64)
+    lib().oracle_filtfilt_fir_nopad_f32(_p(b), _i64(b.size), _p(x), _i64(x.shape[0]),
+                                        _i64(x.shape[1]), _p(y))
+    return y
+
+
+def lfilter_fir(b, x, a0=1.0, zi=None):
+    """SciPy lfilter FIR branch (_signaltools.py:2181-2242). Returns y or (y, zf)."""
+    b = _f32(b); x = _f32(x)
+    y = np.empty(x.shape, dtype=np.float64)
+    k = b.size
+    if zi is None:
+        lib().oracle_lfilter_fir_f32(_p(b), _i64(k), C.c_double(a0), _p(x), _i64(x.shape[0]),
+                                     _i64(x.shape[1]), None, _p(y), None)
+        return y
+    zi = _f32(zi)
+    zf = np.empty((x.shape[0], k - 1), dtype=np.float64)
+    lib().oracle_lfilter_fir_f32(_p(b), _i64(k), C.c_double(a0), _p(x), _i64(x.shape[0]),
+                                 _i64(x.shape[1]), _p(zi), _p(y), _p(zf))
+    return y, zf
+
+
+def upfirdn_out_len(len_h, in_len, up, down):
+    """_output_len (_upfirdn_apply.pyx:59-67), int64."""
+    return int(lib().oracle_upfirdn_out_len(int(len_h), int(in_len), int(up), int(down)))
+
+
+def upfirdn(h, x, up, down, acc64=True):
+    """SciPy upfirdn, mode='constant' (_upfirdn_apply.pyx:421-481)."""
+    h = _f32(h); x = _f32(x)
+    lo = upfirdn_out_len(h.size, x.shape[1], up, down)
+    if acc64:
+        y = np.empty((x.shape[0], lo), dtype=np.float64)
+        fn = lib().oracle_upfirdn_f32_acc64
+    else:
+        y = np.empty((x.shape[0], lo), dtype=np.float32)
+        fn = lib().oracle_upfirdn_f32
+    fn(_p(h), _i64(h.size), _p(x), _i64(x.shape[0]), _i64(x.shape[1]), _i64(up), _i64(down), _p(y))
+    return y
+
+
+def resample_poly_plan(n_in, len_h, up, down):
+    """Integer plan of resample_poly (_signaltools.py:3882-3918)."""
+    p = ResamplePlan()
+    lib().oracle_resample_poly_plan(_i64(n_in), _i64(len_h), _i64(up), _i64(down), C.byref(p))
+    return p.as_dict()
+
+
+def resample_poly(x, up, down, window, acc64=True):
+    """SciPy resample_poly with an array window (_signaltools.py:3865-3957)."""
+    x = _f32(x); window = _f32(window)
+    plan = resample_poly_plan(x.shape[1], window.size, up, down)
+    n_out = x.shape[1] if (plan["up"] == 1 and plan["down"] == 1) else plan["n_out"]
+    y = np.empty((x.shape[0], n_out), dtype=np.float64)
+    lib().oracle_resample_poly_f32(_p(window), _i64(window.size), _i64(up), _i64(down), _p(x),
+                                   _i64(x.shape[0]), _i64(x.shape[1]), C.c_int(1 if acc64 else 0),
+                                   _p(y))
+    return y
+
+
+PAD_NONE, PAD_ODD, PAD_EVEN, PAD_CONSTANT = 0, 1, 2, 3
+
+
+def filtfilt_fir(b, x, padtype=PAD_ODD, padlen=-1):
+    """SciPy filtfilt(b, [1], x, method='pad') (_signaltools.py:4745-4826); f64 sums."""
+    b = _f32(b); x = _f32(x)
+    y = np.empty(x.shape, dtype=np.float64)
+    rc = lib().oracle_filtfilt_fir_f32(_p(b), _i64(b.size), C.c_int(padtype), _i64(padlen), _p(x),
+                                       _i64(x.shape[0]), _i64(x.shape[1]), _p(y))
+    if rc != 0:
+        raise ValueError("The length of the input vector x must be greater than padlen")
+    return y
