@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py -- batched FIR output Gsamples/s on N B200s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1..c5]
+
+A step = one pass of the hot path over one batch of synthetic input.  Default workload is
+BASELINE.json configs[1] ("c2"): lfilter(b, [1], x), 1024 channels x 2^20 samples, 63 taps, f32.
+N > 1: one process per GPU (torchrun), channels sharded across ranks, no data-path collective
+(rows are independent); per-GPU work is fixed => weak scaling, value = all ranks' samples / max time.
+
+One JSON line is printed by rank 0.  Keys beyond the base contract:
+  roofline      algorithmic bytes of the dominant kernel / its CUDA-event launch time, against the
+                measured HBM peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback); `fp32` and
+                `shape_roofline` explain it: this kernel is FP32-issue bound, not HBM bound.
+  cpu_baseline  the CPU restatement of the reference loop (oracle/, kind "port") timed here on the
+                host cores over a bounded row sample.
+  e2e           the same metric through the host-array C-ABI call (pinned host buffers, H2D+kernel+D2H
+                inside the timed region).
+`--impl reference` times the reference's own CPU implementation (its Rust cannot be built here: no
+cargo/rustc, so the oracle port, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched FIR output Gsamples/s"
+UNIT = "Gsamples/s"
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45, BASELINE.md section 2
+
+
+def firwin_np(ntaps, cutoff, window="hamming", beta=5.0):
+    """scipy.signal.firwin(ntaps, cutoff, window=...) for a lowpass, restated with numpy."""
+    m = np.arange(ntaps) - (ntaps - 1) / 2.0
+    h = cutoff * np.sinc(cutoff * m)
+    if window == "hamming":
+        h = h * np.hamming(ntaps)
+    else:
+        h = h * np.kaiser(ntaps, beta)
+    return (h / h.sum()).astype(np.float32)
+
+
+CONFIGS = {
+    # name: rows per GPU, n, description, algorithmic bytes/out, flop/out
+    "c1": dict(rows=64, n=1 << 14, k=31, op="fir", desc="fir_bench default 64x16384 k=31"),
+    "c2": dict(rows=1024, n=1 << 20, k=63, op="lfilter", desc="lfilter a=[1], 1024x2^20, 63 taps"),
+    "c3": dict(rows=256, n=1 << 22, k=4097, op="lfilter", desc="long-tap FIR 256x2^22, 4097 taps"),
+    "c4": dict(rows=2048, n=1 << 20, k=96, op="resample", up=3, down=2, desc="resample_poly 3/2, 2048x2^20, Kaiser 96"),
+    "c5": dict(rows=8192, n=1 << 18, k=255, op="filtfilt", desc="filtfilt FIR 255 taps, 8192x2^18, odd pad"),
+}
+
+
+def make_taps(cfg):
+    if cfg["op"] == "fir":
+        return (1.0 / (np.arange(cfg["k"], dtype=np.float32) + 1.0)).astype(np.float32)      # fir_bench.rs:14-18
+    if cfg["op"] == "lfilter":
+        return firwin_np(cfg["k"], 0.25 if cfg["k"] < 1000 else 0.01)
+    if cfg["op"] == "resample":
+        return firwin_np(cfg["k"], 1.0 / 3.0, window="kaiser")
+    return firwin_np(cfg["k"], 0.2)
+
+
+def algorithmic(cfg, rows):
+    """(out samples, bytes, flops) per step per GPU -- SURVEY.md 8(d) per-output figures."""
+    n, k = cfg["n"], cfg["k"]
+    if cfg["op"] == "resample":
+        n_out = -(-n * cfg["up"] // cfg["down"])
+        outs = rows * n_out
+        return outs, rows * (n * 4 + n_out * 4), outs * 2.0 * k / cfg["up"]
+    outs = rows * n
+    if cfg["op"] == "filtfilt":
+        return outs, outs * 8.0, outs * 2.0 * 2.0 * k
+    return outs, outs * 8.0, outs * 2.0 * k
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if not self.nv:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+            for nme, bit in names.items():
+                if r & bit:
+                    self.reasons.add(nme)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_step(cfg, signal_mod, gpu_mod, x, taps, out):
+    op = cfg["op"]
+    if op == "fir":
+        return gpu_mod.fir1d_batched_f32_cuda(x, taps, out=out)
+    if op == "lfilter":
+        from scir_b200 import _lib as L
+        return gpu_mod.fir1d_batched_f32_cuda(x, taps, out=out, tap_order=L.TAPS_LFILTER)
+    if op == "resample":
+        return signal_mod.resample_poly(x, cfg["up"], cfg["down"], taps)
+    return signal_mod.filtfilt(taps, [1.0], x)
+
+
+def cpu_reference_rate(cfg, taps, threads, budget_s):
+    """Times the oracle port of the reference loop (gpu/lib.rs:1134-1152) over a bounded row sample.
+    Returns (Gsamples/s, rows, seconds)."""
+    from oracle import oracle as O
+    n, k = cfg["n"], cfg["k"]
+    rng = np.random.RandomState(42)
+    # calibrate on one row per thread, then size the sample for ~budget_s
+    rows = max(1, threads)
+    x = (rng.rand(rows, n).astype(np.float32) * 2 - 1)
+    kern_taps = taps if cfg["op"] == "fir" else taps[::-1].copy()    # kernel order = reversed lfilter order
+    t0 = time.perf_counter()
+    O.fir1d_batched_f32_mt(x, kern_taps, threads)
+    dt = time.perf_counter() - t0
+    reps = 1
+    if cfg["op"] == "filtfilt":
+        reps = 2
+    want_rows = int(max(rows, min(rows * budget_s / max(dt * reps, 1e-6), 4096)))
+    want_rows = max(threads, (want_rows // threads) * threads)
+    if want_rows != rows:
+        x = (rng.rand(want_rows, n).astype(np.float32) * 2 - 1)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.fir1d_batched_f32_mt(x, kern_taps, threads)
+    dt = time.perf_counter() - t0
+    return want_rows * n / dt / 1e9, want_rows, dt
+
+
+def reference_arm(args, cfg, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; Rust is not buildable here)."""
+    if rank != 0:
+        return
+    taps = make_taps(cfg)
+    threads = os.cpu_count() or 1
+    if cfg["op"] == "resample":
+        # the reference has no general resampler; its CPU path for this route is the same MAC loop
+        # per output over the polyphase taps: time the FIR port at the per-output tap count
+        eff = dict(cfg, k=cfg["k"] // cfg["up"], op="lfilter")
+        taps = taps[: eff["k"]]
+    else:
+        eff = cfg
+    vals = []
+    per_step_budget = 2.0
+    for _ in range(args.warmup):
+        cpu_reference_rate(eff, taps, threads, 0.3)
+    t_all = time.perf_counter()
+    sample = None
+    for _ in range(args.steps):
+        g, rows, dt = cpu_reference_rate(eff, taps, threads, per_step_budget)
+        vals.append(g)
+        sample = f"{rows} rows x {cfg['n']} samples per step ({dt:.2f} s), extrapolated linearly over rows"
+        if time.perf_counter() - t_all > 150:
+            break
+    v = float(np.median(vals))
+    outs, _, _ = algorithmic(cfg, cfg["rows"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": outs / (v * 1e9) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "config": args.config, "note": "CPU port of gpu/lib.rs:1134-1152, row-parallel"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variant", type=int, default=0)
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.rows:
+        cfg["rows"] = args.rows
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from scir_b200 import _lib as L
+    from scir_b200 import dist as sdist
+    from scir_b200 import gpu, signal
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    rows, n = cfg["rows"], cfg["n"]
+    taps = make_taps(cfg)
+    # weak scaling: every rank owns `rows` channels of a (rows*world)-channel problem
+    r0, r1 = sdist.shard_rows(rows * world, world, rank)
+    assert r1 - r0 == rows
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    x = torch.rand((rows, n), device=dev, generator=g) * 2 - 1
+    out = torch.empty_like(x) if cfg["op"] in ("fir", "lfilter") else None
+    ctx = gpu.torch_context(x)
+    if args.variant:
+        ctx.set_option("variant", args.variant)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        y = run_step(cfg, signal, gpu, x, taps, out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.sample()
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        y = run_step(cfg, signal, gpu, x, taps, out)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    barrier()
+    sampler.sample()
+    clocks = sampler.result()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    outs, abytes, aflops = algorithmic(cfg, rows)
+    value = outs * world / (ms_max * 1e-3) / 1e9
+
+    # ---- per-kernel launch time for the roofline (events on the launching stream) -------------------
+    kern_ms = ms / max(launches / args.steps, 1) if cfg["op"] != "filtfilt" else ms
+    hbm_peak, peak_src = measured_peaks()
+    ffma = C.c_double(0.0)
+    L.lib().scir_b200_microbench_ffma(ctx.handle, 2000, C.byref(ffma))
+    achieved_gbs = abytes / (ms * 1e-3) / 1e9
+    achieved_tf = aflops / (ms * 1e-3) / 1e12
+    t_roof = max(abytes / (hbm_peak * 1e9), aflops / (FP32_NOMINAL_TFLOPS * 1e12))
+    roofline = {
+        "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+        "traffic": TRAFFIC_PER_LAUNCH.get(args.config), "peak_source": peak_src, "kernel_ms": kern_ms,
+        "fp32": {"achieved_tflops": achieved_tf, "peak_nominal_tflops": FP32_NOMINAL_TFLOPS,
+                 "frac_nominal": achieved_tf / FP32_NOMINAL_TFLOPS, "peak_ffma_microbench_tflops": ffma.value,
+                 "frac_of_microbench": achieved_tf / ffma.value if ffma.value else None},
+        "shape_roofline": {"t_ms": t_roof * 1e3, "gsamples": outs / t_roof / 1e9, "frac": (t_roof * 1e3) / ms,
+                           "note": "max(bytes/measured HBM, flops/nominal FP32); this shape is FP32-issue bound"},
+    }
+
+    # ---- e2e: host arrays through the C ABI (pinned buffers, H2D + kernel + D2H timed) ------------------
+    e2e = None
+    if not args.no_e2e and cfg["op"] in ("fir", "lfilter"):
+        lib = L.lib()
+        nbytes = rows * n * 4
+        hx, hy = C.c_void_p(), C.c_void_p()
+        rc1, rc2 = lib.scir_b200_host_alloc(nbytes, C.byref(hx)), lib.scir_b200_host_alloc(nbytes, C.byref(hy))
+        if rc1 == 0 and rc2 == 0:
+            ax = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=(rows, n))
+            ay = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(rows, n))
+            ax[:] = x.cpu().numpy()
+            hctx = gpu.Context(local_rank)
+            order = L.TAPS_SCIR if cfg["op"] == "fir" else L.TAPS_LFILTER
+            e_steps = max(3, min(args.steps, 10))
+            for _ in range(2):
+                gpu.fir1d_batched_f32_cuda(ax, taps, ctx=hctx, out=ay, tap_order=order)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                gpu.fir1d_batched_f32_cuda(ax, taps, ctx=hctx, out=ay, tap_order=order)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / e_steps
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ok = bool(np.allclose(ay[:2], y[:2].cpu().numpy(), atol=1e-6))
+            e2e = {"value": outs * world / float(tt.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                   "d2h_bytes_per_step": nbytes, "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps,
+                   "matches_device_path": ok, "api": "scir_b200_fir1d_batched_f32_host (pinned host buffers)"}
+            lib.scir_b200_host_free(hx)
+            lib.scir_b200_host_free(hy)
+        else:
+            e2e = {"value": None, "unit": UNIT, "error": L.last_error()}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        eff, ctaps = cfg, taps
+        if cfg["op"] == "resample":
+            eff = dict(cfg, k=cfg["k"] // cfg["up"], op="lfilter")
+            ctaps = taps[: eff["k"]]
+        v1, rows1, dt1 = cpu_reference_rate(eff, ctaps, 1, 8.0)
+        threads = os.cpu_count() or 1
+        vn, rowsn, dtn = cpu_reference_rate(eff, ctaps, threads, 8.0)
+        cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{rows1} of {rows} rows x {n} samples ({dt1:.1f} s), rows independent: extrapolated linearly",
+               "all_cores": {"value": vn, "cores": threads, "sample": f"{rowsn} rows ({dtn:.1f} s)"}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "config": args.config, "rows_per_gpu": rows, "n": n, "taps": cfg["k"],
+                       "global_rows": rows * world, "sharding": f"rows x{world}, no collective",
+                       "l2": "inputs larger than L2 (per-step working set >> 126 MB)" if abytes > 3e8 else
+                             "working set fits L2 (latency/plumbing config)",
+                       "variant": args.variant},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` capture of this command (profiles/); None until a capture exists for the config.
+TRAFFIC_PER_LAUNCH = {}
+
+if __name__ == "__main__":
+    main()

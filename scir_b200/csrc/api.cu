@@ -1,0 +1,611 @@
+// api.cu -- C-ABI entry points (include/scir_b200.h): errors, context, memory, and the host-side
+// dispatch that maps scir-signal's FIR routes onto the kernels.  This is the C++ host layer that
+// stands where the reference's `mod cuda` host wrappers stood (crates/scir-gpu/src/lib.rs:840-1113).
+#include "common.cuh"
+
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <numeric>
+
+namespace scir_b200 {
+
+// ---- errors -------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void clear_error() { g_err[0] = '\0'; }
+
+int cuda_error(cudaError_t e, const char* what)
+{
+    int code = SCIR_B200_ERR_LAUNCH;
+    if (e == cudaErrorMemoryAllocation) code = SCIR_B200_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice ||
+        e == cudaErrorInitializationError || e == cudaErrorSystemDriverMismatch ||
+        e == cudaErrorSystemNotReady || e == cudaErrorNotSupported)
+        code = SCIR_B200_ERR_NO_DEVICE;
+    // a sticky error must not poison unrelated later calls' diagnostics
+    cudaGetLastError();
+    return set_error(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+int check_ctx(const scir_b200_ctx* ctx)
+{
+    if (ctx == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "ctx is NULL");
+    return SCIR_B200_OK;
+}
+
+int ctx_bind(const scir_b200_ctx* ctx)
+{
+    SCIR_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return SCIR_B200_OK;
+}
+
+int ctx_scratch(scir_b200_ctx* ctx, DeviceBuffer& buf, size_t bytes)
+{
+    if (buf.bytes >= bytes && buf.ptr != nullptr) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+    if (buf.ptr) {
+        // the old buffer may still be in use by queued work on any of the ctx's streams
+        SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+        if (ctx->s_h2d) SCIR_CUDA(cudaStreamSynchronize(ctx->s_h2d), "cudaStreamSynchronize");
+        if (ctx->s_d2h) SCIR_CUDA(cudaStreamSynchronize(ctx->s_d2h), "cudaStreamSynchronize");
+        SCIR_CUDA(cudaFree(buf.ptr), "cudaFree(scratch)");
+        buf.ptr = nullptr;
+        buf.bytes = 0;
+    }
+    SCIR_CUDA(cudaMalloc(&buf.ptr, bytes), "cudaMalloc(scratch)");
+    buf.bytes = bytes;
+    return SCIR_B200_OK;
+}
+
+int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down)
+{
+    // scipy/signal/_upfirdn_apply.pyx:59-67 (floor division; operands are positive here)
+    return (((in_len - 1) * up + len_h) - 1) / down + 1;
+}
+
+static int check_matrix(const void* p, int64_t ld, int64_t batch, int64_t n, const char* name)
+{
+    if (batch < 0 || n < 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "%s: negative shape", name);
+    if (batch > 0 && n > 0 && p == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "%s is NULL", name);
+    if (batch > 1 && ld < n) return set_error(SCIR_B200_ERR_INVALID_ARG, "%s: ld (%lld) < row length (%lld)",
+                                              name, (long long)ld, (long long)n);
+    return SCIR_B200_OK;
+}
+
+static int check_taps(const float* taps, int64_t k)
+{
+    if (taps == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "taps is NULL");
+    if (k < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "need at least one tap (k=%lld)", (long long)k);
+    if (k > SCIR_B200_MAX_TAPS)
+        return set_error(SCIR_B200_ERR_UNSUPPORTED, "k=%lld exceeds SCIR_B200_MAX_TAPS=%d", (long long)k,
+                         SCIR_B200_MAX_TAPS);
+    return SCIR_B200_OK;
+}
+
+// One causal zero-state FIR over (batch, n): the reference hot path.
+static int fir_causal(scir_b200_ctx* ctx, const float* c, int64_t k, const float* d_x, int64_t ld_x,
+                      float* d_y, int64_t ld_y, int64_t batch, int64_t n)
+{
+    FirPass p{};
+    p.x = d_x; p.y = d_y; p.ld_x = ld_x; p.ld_y = ld_y; p.batch = batch;
+    p.n_x = n; p.n_v = n; p.in_off = 0; p.out_off = 0; p.out_begin = 0; p.out_end = n;
+    p.ext_mode = EXT_NONE; p.bound = BOUND_ZERO; p.dir = +1;
+    if (k >= 1024 && ctx->opt.long_tap_path != 1 && toeplitz_supported(ctx, p, k))
+        return launch_fir_toeplitz(ctx, p, c, k);
+    return launch_fir_pass(ctx, p, c, k);
+}
+
+static int filtfilt_device(scir_b200_ctx* ctx, const float* b, int64_t k, int pad_mode, int64_t padlen,
+                           const float* d_x, int64_t ld_x, float* d_y, int64_t ld_y, int64_t batch,
+                           int64_t n)
+{
+    int64_t edge = 0;
+    int ext = EXT_NONE;
+    int bound = BOUND_HOLD;
+    switch (pad_mode) {
+        case SCIR_B200_PAD_ZERO_STATE: bound = BOUND_ZERO; break;
+        case SCIR_B200_PAD_SCIPY_NONE: break;
+        case SCIR_B200_PAD_ODD: ext = EXT_ODD; edge = padlen < 0 ? 3 * k : padlen; break;
+        case SCIR_B200_PAD_EVEN: ext = EXT_EVEN; edge = padlen < 0 ? 3 * k : padlen; break;
+        case SCIR_B200_PAD_CONSTANT: ext = EXT_CONST; edge = padlen < 0 ? 3 * k : padlen; break;
+        default: return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown pad_mode %d", pad_mode);
+    }
+    if (pad_mode != SCIR_B200_PAD_ZERO_STATE && n <= edge)
+        return set_error(SCIR_B200_ERR_SHAPE,
+                         "The length of the input vector x must be greater than padlen, which is %lld.",
+                         (long long)edge);                       // _signaltools.py:4809
+    if (batch == 0 || n == 0) return SCIR_B200_OK;
+    if (edge == 0) ext = EXT_NONE;
+
+    const int64_t n_v = n + 2 * edge;
+    const int64_t padlead = (4 - edge % 4) % 4;                   // keeps both passes 16-B aligned
+    const int64_t ld1 = (n_v + padlead + 3) / 4 * 4;
+    SCIR_TRY(ctx_scratch(ctx, ctx->scratch, static_cast<size_t>(batch) * ld1 * sizeof(float)));
+    float* y1 = static_cast<float*>(ctx->scratch.ptr);
+
+    FirPass f{};                                                  // forward over the extended signal
+    f.x = d_x; f.ld_x = ld_x; f.y = y1; f.ld_y = ld1; f.batch = batch;
+    f.n_x = n; f.n_v = n_v; f.in_off = -edge; f.out_off = padlead;
+    f.out_begin = 0; f.out_end = n_v; f.ext_mode = ext; f.bound = bound; f.dir = +1;
+    SCIR_TRY(launch_fir_pass(ctx, f, b, k));
+
+    FirPass r{};                                                  // backward, keep [edge, edge+n)
+    r.x = y1; r.ld_x = ld1; r.y = d_y; r.ld_y = ld_y; r.batch = batch;
+    r.n_x = n_v; r.n_v = n_v; r.in_off = padlead; r.out_off = -edge;
+    r.out_begin = edge; r.out_end = edge + n; r.ext_mode = EXT_NONE; r.bound = bound; r.dir = -1;
+    return launch_fir_pass(ctx, r, b, k);
+}
+
+static int resample_plan(int64_t n_in, int64_t len_h, int64_t up, int64_t down, scir_b200_resample_plan* p)
+{
+    // scipy/signal/_signaltools.py:3882-3918, int64 throughout
+    const int64_t g = std::gcd(up, down);
+    up /= g;
+    down /= g;
+    p->up = up;
+    p->down = down;
+    const int64_t prod = n_in * up;
+    p->n_out = prod / down + (prod % down != 0 ? 1 : 0);
+    p->half_len = (len_h - 1) / 2;
+    p->n_pre_pad = down - p->half_len % down;
+    p->n_post_pad = 0;
+    p->n_pre_remove = (p->half_len + p->n_pre_pad) / down;
+    while (upfirdn_out_len(len_h + p->n_pre_pad + p->n_post_pad, n_in, up, down) < p->n_out + p->n_pre_remove)
+        p->n_post_pad += 1;
+    p->len_h_padded = len_h + p->n_pre_pad + p->n_post_pad;
+    p->upfirdn_len = upfirdn_out_len(p->len_h_padded, n_in, up, down);
+    return SCIR_B200_OK;
+}
+
+static int resample_device(scir_b200_ctx* ctx, const float* window, int64_t len_h, int64_t up, int64_t down,
+                           const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
+                           int64_t ld_y)
+{
+    scir_b200_resample_plan pl;
+    resample_plan(n_in, len_h, up, down, &pl);
+    if (batch == 0 || n_in == 0) return SCIR_B200_OK;
+    if (pl.up == 1 && pl.down == 1) {
+        SCIR_TRY(ctx_bind(ctx));
+        SCIR_CUDA(cudaMemcpy2DAsync(d_y, ld_y * sizeof(float), d_x, ld_x * sizeof(float), n_in * sizeof(float),
+                                    batch, cudaMemcpyDeviceToDevice, ctx->stream),
+                  "cudaMemcpy2DAsync(resample copy)");
+        return SCIR_B200_OK;
+    }
+    // h = window * up in f32 (:3909), zero-padded front and back (:3919-3920)
+    std::vector<float> h(static_cast<size_t>(pl.len_h_padded), 0.f);
+    for (int64_t i = 0; i < len_h; ++i) h[static_cast<size_t>(pl.n_pre_pad + i)] = window[i] * static_cast<float>(pl.up);
+    return launch_upfirdn(ctx, h.data(), pl.len_h_padded, pl.up, pl.down, d_x, ld_x, batch, n_in, d_y, ld_y,
+                          pl.n_pre_remove, pl.n_out);
+}
+
+// ---- *_host streaming: rows flow through a 3-slot ring, H2D / kernels / D2H on three streams ---------
+template <typename Fn>
+static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int64_t n_in, float* h_y,
+                         int64_t ld_y, int64_t n_out, int64_t batch, size_t extra_scratch_per_row, Fn&& fn)
+{
+    if (batch == 0) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+    if (!ctx->s_h2d) {
+        SCIR_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate");
+        SCIR_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 3; ++i) {
+            SCIR_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming), "cudaEventCreate");
+            SCIR_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming), "cudaEventCreate");
+            SCIR_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+    }
+    const int64_t ldi = (n_in + 3) / 4 * 4, ldo = (n_out + 3) / 4 * 4;
+    int64_t rows = ctx->opt.host_block_rows;
+    if (rows <= 0) {
+        const size_t per_row = static_cast<size_t>(ldi + ldo) * 4 + extra_scratch_per_row;
+        rows = std::max<int64_t>(1, static_cast<int64_t>((size_t(64) << 20) / std::max<size_t>(per_row, 1)));
+    }
+    rows = std::min(rows, batch);
+    for (int s = 0; s < 3; ++s) {
+        SCIR_TRY(ctx_scratch(ctx, ctx->stage_in[s], static_cast<size_t>(rows) * std::max<int64_t>(ldi, 4) * 4));
+        SCIR_TRY(ctx_scratch(ctx, ctx->stage_out[s], static_cast<size_t>(rows) * std::max<int64_t>(ldo, 4) * 4));
+    }
+    int64_t blk = 0;
+    for (int64_t r0 = 0; r0 < batch; r0 += rows, ++blk) {
+        const int s = static_cast<int>(blk % 3);
+        const int64_t nr = std::min(rows, batch - r0);
+        float* din = static_cast<float*>(ctx->stage_in[s].ptr);
+        float* dout = static_cast<float*>(ctx->stage_out[s].ptr);
+        if (blk >= 3) SCIR_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
+        if (n_in > 0)
+            SCIR_CUDA(cudaMemcpy2DAsync(din, ldi * 4, h_x + r0 * ld_x, ld_x * 4, n_in * 4, nr,
+                                        cudaMemcpyHostToDevice, ctx->s_h2d),
+                      "cudaMemcpy2DAsync(H2D)");
+        SCIR_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->s_h2d), "cudaEventRecord");
+        SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0), "cudaStreamWaitEvent");
+        if (blk >= 3) SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0), "cudaStreamWaitEvent");
+        SCIR_TRY(fn(nr, din, ldi, dout, ldo));
+        SCIR_CUDA(cudaEventRecord(ctx->ev_k[s], ctx->stream), "cudaEventRecord");
+        SCIR_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
+        if (n_out > 0)
+            SCIR_CUDA(cudaMemcpy2DAsync(h_y + r0 * ld_y, ld_y * 4, dout, ldo * 4, n_out * 4, nr,
+                                        cudaMemcpyDeviceToHost, ctx->s_d2h),
+                      "cudaMemcpy2DAsync(D2H)");
+        SCIR_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->s_d2h), "cudaEventRecord");
+    }
+    SCIR_CUDA(cudaStreamSynchronize(ctx->s_d2h), "cudaStreamSynchronize(D2H)");
+    SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    SCIR_CUDA(cudaStreamSynchronize(ctx->s_h2d), "cudaStreamSynchronize(H2D)");
+    return SCIR_B200_OK;
+}
+
+static void reorder_taps(const float* taps, int64_t k, int order, std::vector<float>& c)
+{
+    c.resize(static_cast<size_t>(k));
+    for (int64_t d = 0; d < k; ++d)
+        c[static_cast<size_t>(d)] = (order == SCIR_B200_TAPS_SCIR) ? taps[k - 1 - d] : taps[d];
+}
+
+}  // namespace scir_b200
+
+using namespace scir_b200;
+
+// =====================================================================================================
+extern "C" {
+
+const char* scir_b200_version(void) { return "scir-b200 0.1.0 (sm_100a)"; }
+
+const char* scir_b200_last_error(void) { return g_err; }
+
+int scir_b200_device_count(int* count)
+{
+    if (!count) return set_error(SCIR_B200_ERR_INVALID_ARG, "count is NULL");
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount");
+    *count = n;
+    return SCIR_B200_OK;
+}
+
+static int ctx_make(int device, void* stream, bool borrow, scir_b200_ctx** out)
+{
+    if (!out) return set_error(SCIR_B200_ERR_INVALID_ARG, "ctx out-pointer is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount");
+    if (n == 0) return set_error(SCIR_B200_ERR_NO_DEVICE, "no CUDA device present");
+    if (device < 0 || device >= n)
+        return set_error(SCIR_B200_ERR_NO_DEVICE, "device %d out of range (have %d)", device, n);
+    SCIR_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    SCIR_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return set_error(SCIR_B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only",
+                         device, prop.major, prop.minor);
+    scir_b200_ctx* c = new (std::nothrow) scir_b200_ctx();
+    if (!c) return set_error(SCIR_B200_ERR_OOM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (borrow) {
+        c->stream = static_cast<cudaStream_t>(stream);
+        c->owns_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return cuda_error(e, "cudaStreamCreateWithFlags");
+        }
+        c->owns_stream = true;
+    }
+    *out = c;
+    return SCIR_B200_OK;
+}
+
+int scir_b200_ctx_create(int device, scir_b200_ctx** ctx) { return ctx_make(device, nullptr, false, ctx); }
+
+int scir_b200_ctx_create_on_stream(int device, void* cuda_stream, scir_b200_ctx** ctx)
+{
+    return ctx_make(device, cuda_stream, true, ctx);
+}
+
+int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
+{
+    if (!ctx) return SCIR_B200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
+    if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->stage_in[i].ptr) cudaFree(ctx->stage_in[i].ptr);
+        if (ctx->stage_out[i].ptr) cudaFree(ctx->stage_out[i].ptr);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SCIR_B200_OK;
+}
+
+int scir_b200_ctx_sync(scir_b200_ctx* ctx)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(ctx_bind(ctx));
+    SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_ctx_device(const scir_b200_ctx* ctx, int* device)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!device) return set_error(SCIR_B200_ERR_INVALID_ARG, "device is NULL");
+    *device = ctx->device;
+    return SCIR_B200_OK;
+}
+
+int scir_b200_ctx_stream(const scir_b200_ctx* ctx, void** cuda_stream)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!cuda_stream) return set_error(SCIR_B200_ERR_INVALID_ARG, "cuda_stream is NULL");
+    *cuda_stream = ctx->stream;
+    return SCIR_B200_OK;
+}
+
+static int64_t* option_slot(Options& o, const char* key)
+{
+    if (!key) return nullptr;
+    if (!strcmp(key, "variant")) return &o.variant;
+    if (!strcmp(key, "host_block_rows")) return &o.host_block_rows;
+    if (!strcmp(key, "long_tap_path")) return &o.long_tap_path;
+    if (!strcmp(key, "upfirdn_variant")) return &o.upfirdn_variant;
+    return nullptr;
+}
+
+int scir_b200_ctx_set_option(scir_b200_ctx* ctx, const char* key, int64_t value)
+{
+    SCIR_TRY(check_ctx(ctx));
+    int64_t* s = option_slot(ctx->opt, key);
+    if (!s) return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown option '%s'", key ? key : "(null)");
+    *s = value;
+    return SCIR_B200_OK;
+}
+
+int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t* value)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!value) return set_error(SCIR_B200_ERR_INVALID_ARG, "value is NULL");
+    int64_t* s = option_slot(const_cast<scir_b200_ctx*>(ctx)->opt, key);
+    if (!s) return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown option '%s'", key ? key : "(null)");
+    *value = *s;
+    return SCIR_B200_OK;
+}
+
+int scir_b200_ctx_launch_count(const scir_b200_ctx* ctx, uint64_t* count)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!count) return set_error(SCIR_B200_ERR_INVALID_ARG, "count is NULL");
+    *count = ctx->launches;
+    return SCIR_B200_OK;
+}
+
+// ---- memory ------------------------------------------------------------------------------------------
+int scir_b200_malloc(scir_b200_ctx* ctx, size_t bytes, void** d_ptr)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!d_ptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "d_ptr is NULL");
+    *d_ptr = nullptr;
+    if (bytes == 0) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+    SCIR_CUDA(cudaMalloc(d_ptr, bytes), "cudaMalloc");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_free(scir_b200_ctx* ctx, void* d_ptr)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!d_ptr) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+    SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    SCIR_CUDA(cudaFree(d_ptr), "cudaFree");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_memcpy_h2d(scir_b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (bytes == 0) return SCIR_B200_OK;
+    if (!d_dst || !h_src) return set_error(SCIR_B200_ERR_INVALID_ARG, "memcpy_h2d: NULL pointer");
+    SCIR_TRY(ctx_bind(ctx));
+    SCIR_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(H2D)");
+    SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_memcpy_d2h(scir_b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (bytes == 0) return SCIR_B200_OK;
+    if (!h_dst || !d_src) return set_error(SCIR_B200_ERR_INVALID_ARG, "memcpy_d2h: NULL pointer");
+    SCIR_TRY(ctx_bind(ctx));
+    SCIR_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(D2H)");
+    SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_host_alloc(size_t bytes, void** h_ptr)
+{
+    if (!h_ptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "h_ptr is NULL");
+    *h_ptr = nullptr;
+    if (bytes == 0) return SCIR_B200_OK;
+    SCIR_CUDA(cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable), "cudaHostAlloc");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_host_free(void* h_ptr)
+{
+    if (!h_ptr) return SCIR_B200_OK;
+    SCIR_CUDA(cudaFreeHost(h_ptr), "cudaFreeHost");
+    return SCIR_B200_OK;
+}
+
+// ---- hot path ------------------------------------------------------------------------------------------
+int scir_b200_fir1d_batched_f32(scir_b200_ctx* ctx, const float* d_x, int64_t ld_x, const float* taps, int64_t k,
+                                int tap_order, float* d_y, int64_t ld_y, int64_t batch, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_taps(taps, k));
+    if (tap_order != SCIR_B200_TAPS_SCIR && tap_order != SCIR_B200_TAPS_LFILTER)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    std::vector<float> c;
+    reorder_taps(taps, k, tap_order, c);
+    return fir_causal(ctx, c.data(), k, d_x, ld_x, d_y, ld_y, batch, n);
+}
+
+int scir_b200_fir1d_batched_f32_host(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, const float* taps,
+                                     int64_t k, int tap_order, float* h_y, int64_t ld_y, int64_t batch, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_taps(taps, k));
+    if (tap_order != SCIR_B200_TAPS_SCIR && tap_order != SCIR_B200_TAPS_LFILTER)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
+    SCIR_TRY(check_matrix(h_x, ld_x, batch, n, "x"));
+    SCIR_TRY(check_matrix(h_y, ld_y, batch, n, "y"));
+    if (n == 0) return SCIR_B200_OK;
+    std::vector<float> c;
+    reorder_taps(taps, k, tap_order, c);
+    return host_pipeline(ctx, h_x, ld_x, n, h_y, ld_y, n, batch, 0,
+                         [&](int64_t nr, const float* din, int64_t ldi, float* dout, int64_t ldo) {
+                             return fir_causal(ctx, c.data(), k, din, ldi, dout, ldo, nr, n);
+                         });
+}
+
+int scir_b200_lfilter_fir_f32(scir_b200_ctx* ctx, const float* b, int64_t k, float a0, const float* d_x,
+                              int64_t ld_x, const float* d_zi, float* d_zf, float* d_y, int64_t ld_y,
+                              int64_t batch, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_taps(b, k));
+    if (a0 == 0.f) return set_error(SCIR_B200_ERR_INVALID_ARG, "a[0] must be nonzero");
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    std::vector<float> c(static_cast<size_t>(k));
+    for (int64_t d = 0; d < k; ++d) c[static_cast<size_t>(d)] = b[d] / a0;     // _signaltools.py:2223
+    SCIR_TRY(fir_causal(ctx, c.data(), k, d_x, ld_x, d_y, ld_y, batch, n));
+    if (d_zi) SCIR_TRY(launch_add_zi(ctx, d_y, ld_y, d_zi, batch, n, k));
+    if (d_zf) SCIR_TRY(launch_compute_zf(ctx, c.data(), k, d_x, ld_x, d_zi, d_zf, batch, n));
+    return SCIR_B200_OK;
+}
+
+int64_t scir_b200_upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down)
+{
+    return upfirdn_out_len(len_h, in_len, up, down);
+}
+
+int scir_b200_upfirdn_f32(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
+                          const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y, int64_t ld_y,
+                          int64_t m_begin, int64_t m_count)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!h || len_h < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "h must hold at least one tap");
+    if (up < 1 || down < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "up and down must be >= 1");   // _upfirdn.py:98
+    if (n_in < 1 && batch > 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "upfirdn needs n_in >= 1");
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n_in, "x"));
+    if (m_begin < 0 || m_count < 0 || (batch > 0 && m_begin + m_count > upfirdn_out_len(len_h, n_in, up, down)))
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "output window [%lld, %lld) outside the upfirdn result",
+                         (long long)m_begin, (long long)(m_begin + m_count));
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, m_count, "y"));
+    if (batch == 0 || m_count == 0) return SCIR_B200_OK;
+    return launch_upfirdn(ctx, h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin, m_count);
+}
+
+int scir_b200_resample_poly_plan(int64_t n_in, int64_t len_h, int64_t up, int64_t down,
+                                 scir_b200_resample_plan* plan)
+{
+    if (!plan) return set_error(SCIR_B200_ERR_INVALID_ARG, "plan is NULL");
+    if (up < 1 || down < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "up and down must be >= 1");
+    if (n_in < 1 || len_h < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "n_in and len_h must be >= 1");
+    return resample_plan(n_in, len_h, up, down, plan);
+}
+
+int scir_b200_resample_poly_f32(scir_b200_ctx* ctx, const float* window, int64_t len_h, int64_t up, int64_t down,
+                                const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
+                                int64_t ld_y)
+{
+    SCIR_TRY(check_ctx(ctx));
+    scir_b200_resample_plan pl;
+    if (!window) return set_error(SCIR_B200_ERR_INVALID_ARG, "window is NULL");
+    SCIR_TRY(scir_b200_resample_poly_plan(n_in, len_h, up, down, &pl));
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n_in, "x"));
+    const int64_t n_out = (pl.up == 1 && pl.down == 1) ? n_in : pl.n_out;
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, n_out, "y"));
+    return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y);
+}
+
+int scir_b200_resample_poly_f32_host(scir_b200_ctx* ctx, const float* window, int64_t len_h, int64_t up,
+                                     int64_t down, const float* h_x, int64_t ld_x, int64_t batch, int64_t n_in,
+                                     float* h_y, int64_t ld_y)
+{
+    SCIR_TRY(check_ctx(ctx));
+    scir_b200_resample_plan pl;
+    if (!window) return set_error(SCIR_B200_ERR_INVALID_ARG, "window is NULL");
+    SCIR_TRY(scir_b200_resample_poly_plan(n_in, len_h, up, down, &pl));
+    const int64_t n_out = (pl.up == 1 && pl.down == 1) ? n_in : pl.n_out;
+    SCIR_TRY(check_matrix(h_x, ld_x, batch, n_in, "x"));
+    SCIR_TRY(check_matrix(h_y, ld_y, batch, n_out, "y"));
+    return host_pipeline(ctx, h_x, ld_x, n_in, h_y, ld_y, n_out, batch, 0,
+                         [&](int64_t nr, const float* din, int64_t ldi, float* dout, int64_t ldo) {
+                             return resample_device(ctx, window, len_h, up, down, din, ldi, nr, n_in, dout, ldo);
+                         });
+}
+
+int scir_b200_filtfilt_fir_f32(scir_b200_ctx* ctx, const float* b, int64_t k, int pad_mode, int64_t padlen,
+                               const float* d_x, int64_t ld_x, float* d_y, int64_t ld_y, int64_t batch, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_taps(b, k));
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    return filtfilt_device(ctx, b, k, pad_mode, padlen, d_x, ld_x, d_y, ld_y, batch, n);
+}
+
+int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx* ctx, const float* b, int64_t k, int pad_mode, int64_t padlen,
+                                    const float* h_x, int64_t ld_x, float* h_y, int64_t ld_y, int64_t batch,
+                                    int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_taps(b, k));
+    SCIR_TRY(check_matrix(h_x, ld_x, batch, n, "x"));
+    SCIR_TRY(check_matrix(h_y, ld_y, batch, n, "y"));
+    const size_t extra = static_cast<size_t>(n + 6 * k + 8) * 4;      // the intermediate row
+    return host_pipeline(ctx, h_x, ld_x, n, h_y, ld_y, n, batch, extra,
+                         [&](int64_t nr, const float* din, int64_t ldi, float* dout, int64_t ldo) {
+                             return filtfilt_device(ctx, b, k, pad_mode, padlen, din, ldi, dout, ldo, nr, n);
+                         });
+}
+
+int scir_b200_shard_rows(int64_t batch, int world, int rank, int64_t* row_begin, int64_t* row_end)
+{
+    if (!row_begin || !row_end) return set_error(SCIR_B200_ERR_INVALID_ARG, "row_begin/row_end is NULL");
+    if (batch < 0 || world < 1 || rank < 0 || rank >= world)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "bad shard request (batch=%lld world=%d rank=%d)",
+                         (long long)batch, world, rank);
+    const int64_t base = batch / world, rem = batch % world;
+    *row_begin = rank * base + std::min<int64_t>(rank, rem);
+    *row_end = *row_begin + base + (rank < rem ? 1 : 0);
+    return SCIR_B200_OK;
+}
+
+}  // extern "C"

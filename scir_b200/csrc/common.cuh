@@ -1,0 +1,116 @@
+// common.cuh -- internal declarations shared by the translation units of libscir_b200.so.
+// Not part of the ABI (that is include/scir_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+
+#include "../../include/scir_b200.h"
+
+namespace scir_b200 {
+
+// ---- errors -----------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);          // records thread-local message, returns code
+int cuda_error(cudaError_t e, const char* what);        // maps a CUDA error to an ABI code
+void clear_error();
+
+#define SCIR_CUDA(call, what)                                              \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess) return ::scir_b200::cuda_error(_e, what);   \
+    } while (0)
+
+#define SCIR_TRY(expr)                       \
+    do {                                     \
+        int _rc = (expr);                    \
+        if (_rc != SCIR_B200_OK) return _rc; \
+    } while (0)
+
+// ---- context ----------------------------------------------------------------------------------
+struct Options {
+    int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
+    int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
+    int64_t long_tap_path = 0;  // 0 auto; 1 force FP32 direct; 2 force tcgen05 Toeplitz
+    int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
+};
+
+struct DeviceBuffer {           // RAII-free growable scratch owned by the ctx
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace scir_b200
+
+struct scir_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    uint64_t launches = 0;
+    scir_b200::Options opt;
+    scir_b200::DeviceBuffer scratch;       // filtfilt intermediate etc.
+    // *_host streaming pipeline resources (lazily created)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    scir_b200::DeviceBuffer stage_in[3], stage_out[3];
+    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_out[3] = {nullptr, nullptr, nullptr};
+};
+
+namespace scir_b200 {
+
+int ctx_bind(const scir_b200_ctx* ctx);                                  // cudaSetDevice
+int ctx_scratch(scir_b200_ctx* ctx, DeviceBuffer& buf, size_t bytes);    // grow-only
+int check_ctx(const scir_b200_ctx* ctx);
+
+// ---- the FIR pass: one launch of the direct-form tile kernel -----------------------------------
+// Virtual input sequence v[i], i in [0, n_v): v[i] = ext(x_row)[i + in_off]; outside [0, n_v) the
+// sequence is zero (BOUND_ZERO) or held at its end value (BOUND_HOLD).
+//   dir=+1 (causal):     out[i] = sum_d c[d] * v[i - d]
+//   dir=-1 (anticausal): out[i] = sum_d c[d] * v[i + d]
+// for i in [out_begin, out_end), written to y_row[i + out_off].
+enum { EXT_NONE = 0, EXT_ODD = 1, EXT_EVEN = 2, EXT_CONST = 3 };
+enum { BOUND_ZERO = 0, BOUND_HOLD = 1 };
+
+struct FirPass {
+    const float* x;
+    float* y;
+    long long ld_x, ld_y;
+    long long batch;
+    long long n_x;            // valid underlying indices are [0, n_x) (used by ext modes)
+    long long n_v;            // virtual length
+    long long in_off, out_off;
+    long long out_begin, out_end;
+    int ext_mode;
+    int bound;
+    int dir;
+};
+
+// c: coefficients by delay index (lfilter order), length k.
+int launch_fir_pass(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
+
+// lfilter streaming-state helpers (small kernels)
+int launch_add_zi(scir_b200_ctx* ctx, float* d_y, int64_t ld_y, const float* d_zi, int64_t batch,
+                  int64_t n, int64_t k);
+int launch_compute_zf(scir_b200_ctx* ctx, const float* b, int64_t k, const float* d_x, int64_t ld_x,
+                      const float* d_zi, float* d_zf, int64_t batch, int64_t n);
+
+// ---- polyphase upfirdn ------------------------------------------------------------------------
+int launch_upfirdn(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
+                   const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
+                   int64_t ld_y, int64_t m_begin, int64_t m_count);
+
+// ---- long-tap tensor-core path (tcgen05 block-Toeplitz) -----------------------------------------
+bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k);
+int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
+
+int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace scir_b200

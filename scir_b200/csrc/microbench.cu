@@ -1,0 +1,112 @@
+// microbench.cu -- what THIS box sustains, measured in the same process as the bench so the
+// roofline denominators carry the same clocks: FP32 FFMA issue peak in the exact instruction form
+// the FIR kernel uses (FFMA R, R.reuse, UR, R), and a plain float4 copy for HBM read+write.
+#include "common.cuh"
+
+namespace scir_b200 {
+
+struct MbTaps {
+    float c[64];
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, const __grid_constant__ MbTaps taps)
+{
+    float acc[R];
+    float x[4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = static_cast<float>(r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = 1e-3f * static_cast<float>(threadIdx.x + e);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int t = 0; t < 64; ++t) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(taps.c[t], x[(t + r) & 3], acc[r]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s += acc[r];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // defeat DCE, never true
+}
+
+__global__ void copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4)
+{
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (; i < n4; i += stride) dst[i] = src[i];
+}
+
+}  // namespace scir_b200
+
+using namespace scir_b200;
+
+extern "C" {
+
+int scir_b200_microbench_ffma(scir_b200_ctx* ctx, int iters, double* tflops)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!tflops || iters < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
+    SCIR_TRY(ctx_bind(ctx));
+    constexpr int R = 20;
+    const int blocks = ctx->sm_count * 8;
+    float* d_out = nullptr;
+    SCIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), static_cast<size_t>(blocks) * 256 * 4), "cudaMalloc");
+    MbTaps taps;
+    for (int i = 0; i < 64; ++i) taps.c[i] = 1e-4f * static_cast<float>(i + 1);
+    cudaEvent_t e0, e1;
+    SCIR_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
+    SCIR_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
+    ffma_peak_kernel<R><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps);       // warm-up
+    SCIR_CUDA(cudaEventRecord(e0, ctx->stream), "cudaEventRecord");
+    ffma_peak_kernel<R><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps);
+    SCIR_CUDA(cudaEventRecord(e1, ctx->stream), "cudaEventRecord");
+    SCIR_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+    ctx->launches += 2;
+    float ms = 0.f;
+    SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+    const double flops = 2.0 * blocks * 256.0 * iters * 64.0 * R;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return SCIR_B200_OK;
+}
+
+int scir_b200_microbench_copy(scir_b200_ctx* ctx, size_t bytes, int iters, double* gbps)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!gbps || iters < 1 || bytes < 16) return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
+    SCIR_TRY(ctx_bind(ctx));
+    const size_t n4 = bytes / 16;
+    float4 *a = nullptr, *b = nullptr;
+    SCIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&a), n4 * 16), "cudaMalloc");
+    SCIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&b), n4 * 16), "cudaMalloc");
+    SCIR_CUDA(cudaMemsetAsync(a, 0, n4 * 16, ctx->stream), "cudaMemsetAsync");
+    cudaEvent_t e0, e1;
+    SCIR_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
+    SCIR_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
+    const int blocks = ctx->sm_count * 16;
+    copy_kernel<<<blocks, 512, 0, ctx->stream>>>(a, b, n4);                          // warm-up
+    double best = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        SCIR_CUDA(cudaEventRecord(e0, ctx->stream), "cudaEventRecord");
+        copy_kernel<<<blocks, 512, 0, ctx->stream>>>(a, b, n4);
+        SCIR_CUDA(cudaEventRecord(e1, ctx->stream), "cudaEventRecord");
+        SCIR_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+        float ms = 0.f;
+        SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+        const double g = 2.0 * n4 * 16.0 / (ms * 1e-3) / 1e9;
+        if (g > best) best = g;
+    }
+    ctx->launches += static_cast<uint64_t>(iters) + 1;
+    *gbps = best;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(a);
+    cudaFree(b);
+    return SCIR_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// upfirdn.cu -- polyphase up-FIR-down for sm_100a (SciPy semantics, mode='constant').
+//
+// Spec: scipy/signal/_upfirdn_apply.pyx:421-481.  Closed form evaluated per output m:
+//     t = (m*down) % up,  q = (m*down) / up,   y[m] = sum_{i>=0} h[t + i*up] * x[q - i],
+//     0 <= q-i < n_in,  t + i*up < len_h
+// i.e. the zero-stuffed samples the reference's legacy resampler multiplies by
+// (crates/scir-signal/src/lib.rs:348-352) are never touched.
+#include "common.cuh"
+
+namespace scir_b200 {
+
+// ---- generic kernel: any up/down, one thread per output ------------------------------------------------
+__global__ void upfirdn_generic_kernel(const float* __restrict__ h, long long len_h, long long up, long long down,
+                                       const float* __restrict__ x, long long ld_x, long long batch,
+                                       long long n_in, float* __restrict__ y, long long ld_y, long long m_begin,
+                                       long long m_count)
+{
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= batch * m_count) return;
+    const long long row = gid / m_count;
+    const long long j = gid - row * m_count;
+    const long long md = (m_begin + j) * down;
+    const long long t = md % up;
+    const long long q = md / up;
+    const float* xr = x + row * ld_x;
+    // oldest sample first, like the Cython loop (pyx:451-453)
+    long long imax = (len_h - 1 - t) / up;          // largest i with t + i*up < len_h
+    if (imax > q) imax = q;                         // q - i >= 0
+    float acc = 0.f;
+    for (long long i = imax; i >= 0; --i) {
+        const long long xi = q - i;
+        if (xi < n_in) acc = fmaf(h[t + i * up], xr[xi], acc);
+    }
+    y[row * ld_y + j] = acc;
+}
+
+int launch_upfirdn_generic(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
+                           const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
+                           int64_t ld_y, int64_t m_begin, int64_t m_count)
+{
+    SCIR_TRY(ctx_bind(ctx));
+    float* d_h = nullptr;
+    SCIR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_h), static_cast<size_t>(len_h) * 4, ctx->stream),
+              "cudaMallocAsync(h)");
+    SCIR_CUDA(cudaMemcpyAsync(d_h, h, static_cast<size_t>(len_h) * 4, cudaMemcpyHostToDevice, ctx->stream),
+              "cudaMemcpyAsync(h)");
+    const long long total = batch * m_count;
+    const long long blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return set_error(SCIR_B200_ERR_UNSUPPORTED, "grid too large");
+    upfirdn_generic_kernel<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(
+        d_h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin, m_count);
+    SCIR_CUDA(cudaGetLastError(), "upfirdn_generic_kernel launch");
+    ctx->launches++;
+    SCIR_CUDA(cudaFreeAsync(d_h, ctx->stream), "cudaFreeAsync(h)");
+    return SCIR_B200_OK;
+}
+
+int launch_upfirdn_poly(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
+                        const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y, int64_t ld_y,
+                        int64_t m_begin, int64_t m_count, bool* handled);
+
+int launch_upfirdn(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
+                   const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y, int64_t ld_y,
+                   int64_t m_begin, int64_t m_count)
+{
+    if (ctx->opt.upfirdn_variant != 1) {
+        bool handled = false;
+        SCIR_TRY(launch_upfirdn_poly(ctx, h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin,
+                                     m_count, &handled));
+        if (handled) return SCIR_B200_OK;
+    }
+    return launch_upfirdn_generic(ctx, h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin, m_count);
+}
+
+}  // namespace scir_b200

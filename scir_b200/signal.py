@@ -1,0 +1,235 @@
+"""Host-side mirror of crate `scir-signal`'s FIR routes onto the GPU path.
+
+    gpu.fir1d_batched_f32(x, taps, device)   crates/scir-signal/src/lib.rs:365-375 (forwarder)
+    lfilter(b, a, x)           a = [a0]      SciPy spec: scipy/signal/_signaltools.py:2181-2242
+    upfirdn(h, x, up, down)                  scipy/signal/_upfirdn.py:107-216, _upfirdn_apply.pyx:421-481
+    resample_poly(x, up, down, window=h)     scipy/signal/_signaltools.py:3865-3957
+    filtfilt(b, a, x, padtype, padlen)       scipy/signal/_signaltools.py:4745-4826 (FIR numerator)
+    filtfilt_zero_state(b, x)                the reference's own structure, sig/lib.rs:278-291
+
+The reference has only the forwarder; `resample_poly` there is f64, 2/3-only (sig/lib.rs:313-362)
+and `filtfilt` is SOS-only, so SciPy -- which the reference's fixtures are generated from
+(scripts/gen_signal_fixtures.py) -- is the behavioural spec.  All dispatch logic
+(tap reversal, gcd reduction, pad plan, odd extension, zi) lives in C++ behind the C ABI; this file
+only marshals arrays.  Inputs are (batch, n) or (n,) float32; numpy => *_host ABI calls, torch CUDA
+tensors => device-pointer ABI calls on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from . import gpu as G
+from .gpu import Device, GpuError, _check, _is_torch, _load, _ptr, _taps_f32
+
+
+class gpu:  # noqa: N801  (mirrors `pub mod gpu` in scir-signal)
+    @staticmethod
+    def fir1d_batched_f32(x, taps, device: Device, **kw):
+        """sig/lib.rs:372-374"""
+        return G.fir1d_batched_f32_auto(x, taps, device, **kw)
+
+
+def _as_2d(x):
+    """Returns (array2d, was_1d)."""
+    if _is_torch(x):
+        return (x[None, :], True) if x.dim() == 1 else (x, False)
+    a = np.asarray(x, dtype=np.float32)
+    return (a[None, :], True) if a.ndim == 1 else (a, False)
+
+
+def _prep(x2):
+    """(device?, obj, ptr, ld, batch, n, ctx)"""
+    if _is_torch(x2):
+        xt, ld = G._torch_matrix(x2)
+        return True, xt, xt.data_ptr(), ld, xt.shape[0], xt.shape[1], G.torch_context(xt)
+    a = G._host_matrix(x2)
+    return False, a, _ptr(a), max(a.shape[1], 1), a.shape[0], a.shape[1], G.default_context(0)
+
+
+def _alloc_like(dev, ref, batch, n_out):
+    if dev:
+        import torch
+        y = torch.empty((batch, n_out), dtype=torch.float32, device=ref.device)
+        return y, y.data_ptr(), max(n_out, 1)
+    y = np.empty((batch, n_out), dtype=np.float32)
+    return y, _ptr(y), max(n_out, 1)
+
+
+class _DevBuf:
+    """Library-owned device buffer for the host-array variants that have no *_host ABI twin."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.p = ctx, C.c_void_p()
+        _check(_load().scir_b200_malloc(ctx.handle, max(int(nbytes), 4), C.byref(self.p)))
+
+    def upload(self, a: np.ndarray):
+        _check(_load().scir_b200_memcpy_h2d(self.ctx.handle, self.p, _ptr(a), a.nbytes))
+        return self
+
+    def download(self, a: np.ndarray):
+        _check(_load().scir_b200_memcpy_d2h(self.ctx.handle, _ptr(a), self.p, a.nbytes))
+        return a
+
+    def free(self):
+        _check(_load().scir_b200_free(self.ctx.handle, self.p))
+
+
+def lfilter(b, a, x, zi=None, *, ctx=None):
+    """lfilter(b, [a0], x[, zi]) along the last axis.  Returns y, or (y, zf) when zi is given."""
+    a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+    if a.size != 1:
+        raise GpuError.backend_unavailable("only FIR (len(a) == 1) filters run on this path; IIR stays on the CPU")
+    bt = _taps_f32(b)
+    x2, was1d = _as_2d(x)
+    dev, xo, xp, ld, batch, n, c = _prep(x2)
+    c = ctx or c
+    y, yp, ldy = _alloc_like(dev, xo, batch, n)
+    lib = _load()
+    if zi is None:
+        _check(lib.scir_b200_lfilter_fir_f32(c.handle, _ptr(bt), bt.size, float(a[0]), xp, ld, None, None,
+                                             yp, ldy, batch, n))
+        return y[0] if was1d else y
+    if not dev:
+        km1 = bt.size - 1
+        zih = np.ascontiguousarray(zi, dtype=np.float32).reshape(batch, km1)
+        zfh = np.empty_like(zih)
+        bufs = [_DevBuf(c, xo.nbytes).upload(xo), _DevBuf(c, zih.nbytes).upload(zih),
+                _DevBuf(c, zih.nbytes), _DevBuf(c, xo.nbytes)]
+        try:
+            _check(lib.scir_b200_lfilter_fir_f32(c.handle, _ptr(bt), bt.size, float(a[0]), bufs[0].p, ld,
+                                                 bufs[1].p if km1 else None, bufs[2].p if km1 else None,
+                                                 bufs[3].p, ldy, batch, n))
+            c.sync()
+            bufs[3].download(y)
+            if km1:
+                bufs[2].download(zfh)
+        finally:
+            for bf in bufs:
+                bf.free()
+        return (y[0], zfh[0]) if was1d else (y, zfh)
+    import torch
+    zit = zi.reshape(batch, bt.size - 1).contiguous().to(torch.float32)
+    zf = torch.empty_like(zit)
+    _check(lib.scir_b200_lfilter_fir_f32(c.handle, _ptr(bt), bt.size, float(a[0]), xp, ld,
+                                         zit.data_ptr() if zit.numel() else None,
+                                         zf.data_ptr() if zf.numel() else None, yp, ldy, batch, n))
+    return (y[0], zf[0]) if was1d else (y, zf)
+
+
+def upfirdn_output_len(len_h, in_len, up, down) -> int:
+    """_output_len, _upfirdn_apply.pyx:59-67"""
+    return int(_load().scir_b200_upfirdn_out_len(int(len_h), int(in_len), int(up), int(down)))
+
+
+def upfirdn(h, x, up=1, down=1, *, ctx=None):
+    """upfirdn(h, x, up, down, mode='constant') along the last axis; f32 in, f32 out."""
+    if int(up) != up or int(down) != down:
+        raise ValueError("up and down must be integers")                     # _upfirdn.py:95-97
+    up, down = int(up), int(down)
+    if up < 1 or down < 1:
+        raise ValueError("Both up and down must be >= 1")                    # _upfirdn.py:98
+    ht = _taps_f32(h)
+    x2, was1d = _as_2d(x)
+    dev, xo, xp, ld, batch, n, c = _prep(x2)
+    c = ctx or c
+    if n < 1:
+        raise ValueError("x must have at least one sample")
+    lo = upfirdn_output_len(ht.size, n, up, down)
+    if dev:
+        y, yp, ldy = _alloc_like(dev, xo, batch, lo)
+        _check(_load().scir_b200_upfirdn_f32(c.handle, _ptr(ht), ht.size, up, down, xp, ld, batch, n, yp, ldy,
+                                             0, lo))
+        return y[0] if was1d else y
+    y = np.empty((batch, lo), dtype=np.float32)
+    bx, by = _DevBuf(c, xo.nbytes).upload(xo), _DevBuf(c, y.nbytes)
+    try:
+        _check(_load().scir_b200_upfirdn_f32(c.handle, _ptr(ht), ht.size, up, down, bx.p, ld, batch, n, by.p,
+                                             max(lo, 1), 0, lo))
+        c.sync()
+        by.download(y)
+    finally:
+        bx.free()
+        by.free()
+    return y[0] if was1d else y
+
+
+def resample_poly_plan(n_in, len_h, up, down) -> dict:
+    """The int64 plan of resample_poly (_signaltools.py:3882-3918); bit-exact with SciPy."""
+    p = L.ResamplePlan()
+    _check(_load().scir_b200_resample_poly_plan(int(n_in), int(len_h), int(up), int(down), C.byref(p)))
+    return p.as_dict()
+
+
+def kaiser_lowpass(up: int, down: int) -> np.ndarray:
+    """SciPy's default resample_poly design (_signaltools.py:3898-3904):
+    firwin(2*10*max(up,down)+1, 1/max(up,down), window=('kaiser', 5.0)), restated with numpy so the
+    default works without SciPy.  Host-side, a few hundred taps."""
+    g = math.gcd(int(up), int(down))
+    max_rate = max(int(up) // g, int(down) // g)
+    ntaps = 2 * 10 * max_rate + 1
+    cutoff = 1.0 / max_rate
+    m = np.arange(ntaps) - (ntaps - 1) / 2.0
+    h = cutoff * np.sinc(cutoff * m) * np.kaiser(ntaps, 5.0)
+    return (h / h.sum()).astype(np.float64)
+
+
+def resample_poly(x, up, down, window=("kaiser", 5.0), *, ctx=None):
+    """resample_poly(x, up, down, window) along the last axis, padtype='constant' (cval 0)."""
+    if int(up) != up or int(down) != down:
+        raise ValueError("up and down must be integers")
+    up, down = int(up), int(down)
+    if up < 1 or down < 1:
+        raise ValueError("up and down must be >= 1")                         # :3876-3877
+    if isinstance(window, (tuple, str)):
+        if window != ("kaiser", 5.0):
+            raise GpuError.backend_unavailable("pass the filter as an array; only the default "
+                                               "('kaiser', 5.0) design is built in")
+        window = kaiser_lowpass(up, down)
+    w = _taps_f32(window)
+    x2, was1d = _as_2d(x)
+    dev, xo, xp, ld, batch, n, c = _prep(x2)
+    c = ctx or c
+    plan = resample_poly_plan(n, w.size, up, down)
+    n_out = n if (plan["up"] == 1 and plan["down"] == 1) else plan["n_out"]
+    y, yp, ldy = _alloc_like(dev, xo, batch, n_out)
+    fn = _load().scir_b200_resample_poly_f32 if dev else _load().scir_b200_resample_poly_f32_host
+    _check(fn(c.handle, _ptr(w), w.size, up, down, xp, ld, batch, n, yp, ldy))
+    return y[0] if was1d else y
+
+
+_PAD = {"odd": L.PAD_ODD, "even": L.PAD_EVEN, "constant": L.PAD_CONSTANT, None: L.PAD_SCIPY_NONE}
+
+
+def _filtfilt(b, x, mode, padlen, ctx):
+    bt = _taps_f32(b)
+    x2, was1d = _as_2d(x)
+    dev, xo, xp, ld, batch, n, c = _prep(x2)
+    c = ctx or c
+    y, yp, ldy = _alloc_like(dev, xo, batch, n)
+    fn = _load().scir_b200_filtfilt_fir_f32 if dev else _load().scir_b200_filtfilt_fir_f32_host
+    rc = fn(c.handle, _ptr(bt), bt.size, mode, -1 if padlen is None else int(padlen), xp, ld, yp, ldy, batch, n)
+    if rc == L.ERR_SHAPE:
+        raise ValueError(L.last_error())                                     # SciPy raises ValueError, :4809
+    _check(rc)
+    return y[0] if was1d else y
+
+
+def filtfilt(b, a, x, padtype="odd", padlen=None, *, ctx=None):
+    """filtfilt(b, [1], x, padtype, padlen), method='pad', along the last axis."""
+    a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+    if a.size != 1:
+        raise GpuError.backend_unavailable("only FIR numerators (a = [a0]) run on this path")
+    if padtype not in _PAD:
+        raise ValueError(f"Unknown value '{padtype}' given to padtype.")       # :4795-4797
+    bt = _taps_f32(b) / np.float32(a[0])
+    return _filtfilt(bt, x, _PAD[padtype], padlen, ctx)
+
+
+def filtfilt_zero_state(b, x, *, ctx=None):
+    """The reference's filtfilt structure (sig/lib.rs:278-291) with an FIR numerator: zero-state
+    forward pass, zero-state pass over the reversed result, reverse.  No padding."""
+    return _filtfilt(b, x, L.PAD_ZERO_STATE, None, ctx)
