@@ -385,6 +385,10 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
 {
     SCIR_TRY(check_ctx(ctx));
     if (!value) return set_error(SCIR_B200_ERR_INVALID_ARG, "value is NULL");
+    if (key && !strcmp(key, "poly_launches")) {                       // read-only statistic
+        *value = static_cast<int64_t>(ctx->poly_launches);
+        return SCIR_B200_OK;
+    }
     int64_t* s = option_slot(const_cast<scir_b200_ctx*>(ctx)->opt, key);
     if (!s) return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown option '%s'", key ? key : "(null)");
     *value = *s;

@@ -52,6 +52,7 @@ struct scir_b200_ctx {
     int sm_count = 0;
     int max_smem_optin = 0;
     uint64_t launches = 0;
+    uint64_t poly_launches = 0;            // launches served by the polyphase TILE kernel (tests)
     scir_b200::Options opt;
     scir_b200::DeviceBuffer scratch;       // filtfilt intermediate etc.
     // *_host streaming pipeline resources (lazily created)

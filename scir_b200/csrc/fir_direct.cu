@@ -28,6 +28,9 @@
 // extension are properties of the tile LOADER (edge tiles only); interior tiles always take the
 // bulk-copy path.  See DESIGN.md section 4.
 #include "common.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
 
 namespace scir_b200 {
 
@@ -44,62 +47,6 @@ struct FirTileParams {
     int in_vec_ok;        // input rows are 16-B aligned => interior tiles may use the bulk copy
     int out_vec_ok;       // same for the output side
 };
-
-// ---- PTX helpers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
-                                              uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(dst_smem),
-        "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_copy_s2g(void* dst, uint32_t src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                 "r"(src_smem), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
 
 // ---- virtual input sequence (edge tiles only) ------------------------------------------------------
 __device__ __forceinline__ float vload(const FirPass& p, const float* __restrict__ xr, long long i)
@@ -127,7 +74,37 @@ __device__ __forceinline__ float vload(const FirPass& p, const float* __restrict
     return xr[u];
 }
 
-// ---- the tile kernel -------------------------------------------------------------------------------
+// ---- the FFMA core: R outputs per thread, x-major over the window, taps from uniform registers ------
+// causal:     wbase points at v[t0] (smem index DP + tid*R); chunk c uses samples t0 + r - d, d in [c*KC,(c+1)*KC)
+// anticausal: wbase points at v[t0] (smem index tid*R);      chunk c uses samples t0 + r + d
+template <int KC, int R, int DIR, int MAXK>
+__device__ __forceinline__ void fir_core(float (&acc)[R], const float* wbase, int nchunk, const TapsParam<MAXK>& taps)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+        const float4* w = reinterpret_cast<const float4*>((DIR > 0) ? (wbase - (c + 1) * KC) : (wbase + c * KC));
+        const float* tc = taps.c + c * KC;
+#pragma unroll
+        for (int v4 = 0; v4 < (KC + R) / 4; ++v4) {
+            const float4 v = w[v4];
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = 4 * v4 + e;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    // causal: sample index (rel. to t0) = s - KC  => local delay = r - (s - KC)
+                    // anticausal: sample index = s                => local delay = s - r
+                    const int dl = (DIR > 0) ? (r + KC - s) : (s - r);
+                    if (dl >= 0 && dl < KC) acc[r] = fmaf(tc[dl], xv[e], acc[r]);
+                }
+            }
+        }
+    }
+}
+
+// ---- one tile per CTA (variant 3; the round-1 first cut, kept for A/B profiling) ---------------------
 // KC taps per chunk, R outputs per thread, NT threads, DIR +1 causal / -1 anticausal.
 template <int KC, int R, int NT, int DIR, int MAXK>
 __global__ void __launch_bounds__(NT, (NT <= 128) ? 8 : 4)
@@ -169,34 +146,8 @@ fir_tile_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__
         __syncthreads();
     }
 
-    // ---- R outputs per thread, x-major over the window, taps from uniform registers -----------------
     float acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.f;
-
-    // causal:     smem index of v[i0 + j] is DP + j; chunk c uses samples t0 + r - d, d in [c*KC,(c+1)*KC)
-    // anticausal: smem index of v[i0 + j] is j;      chunk c uses samples t0 + r + d
-    const float* wbase = (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R);
-    for (int c = 0; c < q.nchunk; ++c) {
-        const float4* w = reinterpret_cast<const float4*>((DIR > 0) ? (wbase - (c + 1) * KC) : (wbase + c * KC));
-        const float* tc = taps.c + c * KC;
-#pragma unroll
-        for (int v4 = 0; v4 < (KC + R) / 4; ++v4) {
-            const float4 v = w[v4];
-            const float xv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int s = 4 * v4 + e;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    // causal: sample index (rel. to t0) = s - KC  => local delay = r - (s - KC)
-                    // anticausal: sample index = s                => local delay = s - r
-                    const int dl = (DIR > 0) ? (r + KC - s) : (s - r);
-                    if (dl >= 0 && dl < KC) acc[r] = fmaf(tc[dl], xv[e], acc[r]);
-                }
-            }
-        }
-    }
+    fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R), q.nchunk, taps);
 
     // ---- results back through shared memory, then one bulk store --------------------------------------
     __syncthreads();                                       // every warp is done reading the tile
@@ -210,7 +161,7 @@ fir_tile_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__
         __syncthreads();
         if (tid == 0) {
             bulk_copy_s2g(yr + i0 + p.out_off, smem_u32(smem), TILE * 4u);
-            bulk_store_wait_read();                        // smem must outlive the read
+            bulk_store_wait_read<0>();                        // smem must outlive the read
         }
     } else {
         __syncthreads();
@@ -219,6 +170,124 @@ fir_tile_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__
             if (i >= p.out_begin && i < p.out_end) yr[i + p.out_off] = smem[s];
         }
     }
+}
+
+// ---- the streaming kernel (default): persistent CTAs, double-buffered TMA bulk loads ------------------
+// Each CTA walks tiles w = blockIdx.x, +gridDim.x, ... of the (row, tile) grid.  Two input stages are
+// filled by cp.async.bulk two tiles ahead (full[] mbarriers, one elected thread), results leave
+// through a third buffer and a bulk store that drains while the next tile is being computed.  The
+// per-tile cost outside the FFMA stream is two CTA barriers, five STS.128 and a dozen scalar
+// instructions; index set-up, barrier init and the first DRAM round trip are paid once per CTA
+// instead of once per tile.
+struct TileCoord {
+    long long row, tile;
+};
+
+template <int KC, int R, int NT, int DIR, int MAXK>
+__global__ void __launch_bounds__(NT, 3)
+fir_stream_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__ TapsParam<MAXK> taps)
+{
+    static_assert(KC % 4 == 0 && R % 4 == 0, "vector width");
+    static_assert((R / 4) % 2 == 1, "R/4 must be odd: conflict-free LDS.128 on a dense tile");
+    constexpr int TILE = NT * R;
+    extern __shared__ __align__(128) float smem[];     // in[0] | in[1] | out
+    __shared__ __align__(8) unsigned long long full[2];
+
+    const FirPass& p = q.p;
+    const int tid = threadIdx.x;
+    const int DP = q.nchunk * KC;
+    const int len = DP + TILE;
+    float* const out_s = smem + 2 * len;
+    const uint32_t bar0 = smem_u32(&full[0]);              // full[s] lives at bar0 + 8*s
+    const long long G = gridDim.x;
+    const long long step_row = G / q.ntiles, step_tile = G - step_row * q.ntiles;
+
+    auto advance = [&](TileCoord& t) {
+        t.row += step_row;
+        t.tile += step_tile;
+        if (t.tile >= q.ntiles) {
+            t.tile -= q.ntiles;
+            t.row += 1;
+        }
+    };
+    auto first_sample = [&](const TileCoord& t) {          // virtual index of the first staged sample
+        const long long i0 = q.base0 + t.tile * TILE;
+        return (DIR > 0) ? (i0 - DP) : i0;
+    };
+    auto can_bulk = [&](long long a) {
+        bool ok = q.in_vec_ok && a >= 0 && a + len <= p.n_v;
+        if (p.ext_mode != EXT_NONE) ok = ok && (a + p.in_off >= 0) && (a + p.in_off + len <= p.n_x);
+        return ok;
+    };
+    auto prefetch = [&](const TileCoord& t, int s) {       // thread 0 only
+        if (t.row >= p.batch) return;
+        const long long a = first_sample(t);
+        if (!can_bulk(a)) return;
+        mbar_arrive_expect_tx(bar0 + 8u * s, static_cast<uint32_t>(len) * 4u);
+        bulk_copy_g2s(smem_u32(smem + s * len), p.x + t.row * p.ld_x + a + p.in_off, static_cast<uint32_t>(len) * 4u,
+                      bar0 + 8u * s);
+    };
+
+    TileCoord cur;
+    cur.row = blockIdx.x / q.ntiles;
+    cur.tile = blockIdx.x - cur.row * q.ntiles;
+    TileCoord nxt = cur;                                   // runs two tiles ahead of cur
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_mbar_init();
+        prefetch(nxt, 0);
+        advance(nxt);
+        prefetch(nxt, 1);
+        advance(nxt);
+    } else {
+        advance(nxt);
+        advance(nxt);
+    }
+    __syncthreads();                                       // barrier init visible to the waiters
+
+    uint32_t phases = 0;                                   // bit s = parity to wait for on full[s]
+    for (int it = 0; cur.row < p.batch; ++it, advance(cur), advance(nxt)) {
+        const int s = it & 1;
+        const long long i0 = q.base0 + cur.tile * TILE;
+        const long long a = (DIR > 0) ? (i0 - DP) : i0;
+        const float* __restrict__ xr = p.x + cur.row * p.ld_x;
+        float* __restrict__ yr = p.y + cur.row * p.ld_y;
+        float* const in = smem + s * len;
+
+        if (can_bulk(a)) {
+            mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
+            phases ^= 1u << s;
+        } else {                                           // edge tile: zero / held / extended samples
+            for (int t = tid; t < len; t += NT) in[t] = vload(p, xr, a + t);
+            __syncthreads();
+        }
+
+        float acc[R];
+        fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.nchunk, taps);
+
+        if (tid == 0) bulk_store_wait_read<0>();           // the previous tile's store has drained `out`
+        __syncthreads();                                   // A: in[s] consumed by every warp, out free
+        if (tid == 0) prefetch(nxt, s);                    // refill in[s] two tiles ahead
+
+        float4* so = reinterpret_cast<float4*>(out_s + tid * R);
+#pragma unroll
+        for (int r = 0; r < R; r += 4) so[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+
+        const bool bulk_out = q.out_vec_ok && i0 >= p.out_begin && i0 + TILE <= p.out_end;
+        if (bulk_out) {
+            fence_proxy_async_smem();                      // generic-proxy writes -> async proxy
+            __syncthreads();                               // B
+            if (tid == 0) bulk_copy_s2g(yr + i0 + p.out_off, smem_u32(out_s), TILE * 4u);
+        } else {
+            __syncthreads();
+            for (int t = tid; t < TILE; t += NT) {
+                const long long i = i0 + t;
+                if (i >= p.out_begin && i < p.out_end) yr[i + p.out_off] = out_s[t];
+            }
+        }
+    }
+    if (tid == 0) bulk_store_wait_read<0>();               // smem must outlive the last store's read
 }
 
 // ---- naive kernel: one thread per output, taps from global memory ------------------------------------
@@ -279,23 +348,44 @@ constexpr int kSmallK = 256;
 constexpr int kBigK = SCIR_B200_MAX_TAPS;
 
 template <int KC, int DIR, int MAXK>
-int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int64_t k, size_t smem_bytes,
-                long long grid)
+int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int64_t k, long long total)
 {
     // zero-padded host staging; the launch copies it into the parameter buffer synchronously
     thread_local TapsParam<MAXK>* tl = nullptr;
     if (!tl) tl = new TapsParam<MAXK>();
     for (int i = 0; i < MAXK; ++i) tl->c[i] = (i < k) ? c[i] : 0.f;
-    auto kern = fir_tile_kernel<KC, kR, kNT, DIR, MAXK>;
-    static thread_local size_t configured[16] = {0};
-    if (smem_bytes > 48 * 1024 && configured[ctx->device & 15] < smem_bytes) {
+    const size_t len = static_cast<size_t>(q.nchunk) * KC + kTile;
+    const bool stream = (ctx->opt.variant != 3);
+    const size_t smem_bytes = (stream ? (2 * len + kTile) : len) * sizeof(float);
+    if (smem_bytes > static_cast<size_t>(ctx->max_smem_optin))
+        return set_error(SCIR_B200_ERR_UNSUPPORTED, "tile needs %zu B of shared memory", smem_bytes);
+    auto kern = stream ? fir_stream_kernel<KC, kR, kNT, DIR, MAXK> : fir_tile_kernel<KC, kR, kNT, DIR, MAXK>;
+    // per (thread, device, kernel flavour): opt-in shared memory and the resident-CTA count
+    static thread_local size_t configured[16][2] = {};
+    static thread_local int resident[16][2] = {};
+    const int d = ctx->device & 15, f = stream ? 1 : 0;
+    if (configured[d][f] < smem_bytes || resident[d][f] == 0) {
         SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem_bytes)),
-                  "cudaFuncSetAttribute(fir_tile_kernel)");
-        configured[ctx->device & 15] = smem_bytes;
+                                       static_cast<int>(std::max<size_t>(smem_bytes, configured[d][f]))),
+                  "cudaFuncSetAttribute(fir kernel)");
+        configured[d][f] = std::max<size_t>(smem_bytes, configured[d][f]);
+        resident[d][f] = -1;
+    }
+    long long grid = total;
+    if (stream) {
+        // persistent grid: every SM holds as many CTAs as fit; each walks tiles with stride gridDim.x
+        static thread_local size_t occ_smem[16] = {};
+        if (resident[d][f] <= 0 || occ_smem[d] != smem_bytes) {
+            int nb = 0;
+            SCIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kNT, smem_bytes),
+                      "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            resident[d][f] = std::max(nb, 1);
+            occ_smem[d] = smem_bytes;
+        }
+        grid = std::min<long long>(total, static_cast<long long>(ctx->sm_count) * resident[d][f]);
     }
     kern<<<static_cast<unsigned>(grid), kNT, smem_bytes, ctx->stream>>>(q, *tl);
-    SCIR_CUDA(cudaGetLastError(), "fir_tile_kernel launch");
+    SCIR_CUDA(cudaGetLastError(), "fir kernel launch");
     ctx->launches++;
     return SCIR_B200_OK;
 }
@@ -341,19 +431,16 @@ int launch_fir_pass(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int
     q.ntiles = (pass.out_end - q.base0 + kTile - 1) / kTile;
     const long long grid = q.ntiles * pass.batch;
     if (grid > 0x7fffffffLL) return set_error(SCIR_B200_ERR_UNSUPPORTED, "grid too large (%lld tiles)", grid);
-    const size_t smem_bytes = static_cast<size_t>(DP + kTile) * sizeof(float);
-    if (smem_bytes > static_cast<size_t>(ctx->max_smem_optin))
-        return set_error(SCIR_B200_ERR_UNSUPPORTED, "tile needs %zu B of shared memory", smem_bytes);
 
     const bool small = (DP <= kSmallK);
     if (pass.dir > 0) {
-        if (KC == 32) return launch_tile<32, +1, kSmallK>(ctx, q, c, k, smem_bytes, grid);
-        if (small) return launch_tile<64, +1, kSmallK>(ctx, q, c, k, smem_bytes, grid);
-        return launch_tile<64, +1, kBigK>(ctx, q, c, k, smem_bytes, grid);
+        if (KC == 32) return launch_tile<32, +1, kSmallK>(ctx, q, c, k, grid);
+        if (small) return launch_tile<64, +1, kSmallK>(ctx, q, c, k, grid);
+        return launch_tile<64, +1, kBigK>(ctx, q, c, k, grid);
     } else {
-        if (KC == 32) return launch_tile<32, -1, kSmallK>(ctx, q, c, k, smem_bytes, grid);
-        if (small) return launch_tile<64, -1, kSmallK>(ctx, q, c, k, smem_bytes, grid);
-        return launch_tile<64, -1, kBigK>(ctx, q, c, k, smem_bytes, grid);
+        if (KC == 32) return launch_tile<32, -1, kSmallK>(ctx, q, c, k, grid);
+        if (small) return launch_tile<64, -1, kSmallK>(ctx, q, c, k, grid);
+        return launch_tile<64, -1, kBigK>(ctx, q, c, k, grid);
     }
 }
 

@@ -1,13 +1,284 @@
-// upfirdn_poly.cu -- tiled polyphase kernel (placeholder until the tile kernel lands: declines).
+// upfirdn_poly.cu -- tiled polyphase up-FIR-down kernel for sm_100a (SciPy semantics, mode='constant').
+//
+// Spec: scipy/signal/_upfirdn_apply.pyx:421-481 / _upfirdn.py:47-64.  Output m of a row is
+//     y[m] = sum_i h[t + i*up] * x[q - i],   t = (m*down) % up,  q = (m*down) / up
+// so only the `1/up` of the taps that meet a real sample are ever multiplied -- the reference's
+// legacy resampler (crates/scir-signal/src/lib.rs:348-360) multiplies every stuffed zero and then
+// throws away 2 of 3 results.
+//
+// Same execution model as fir_direct.cu (FFMA-issue bound, so everything else is kept off the compute
+// warps), extended to a rational rate:
+//   * the phase pattern repeats every `up` outputs / `down` inputs, so a thread owns R = up*G
+//     consecutive outputs starting at a multiple of `up`: phase t_j and input offset dq_j of its
+//     j-th output are COMPILE-TIME constants, and the x-major sliding window is fully unrolled with
+//     taps as constant-bank / uniform-register FFMA operands.
+//   * per-thread input stride is down*G floats; G is chosen per (up, down) so that stride is a
+//     multiple of 4 with an odd quotient: 16-B aligned, bank-conflict-free LDS.128 on a DENSE tile,
+//     which is what allows the tile + halo to arrive by ONE 1-D TMA bulk copy.
+//   * Z = number of leading zero taps (< up): resample_poly pads the filter in front
+//     (_signaltools.py:3912-3920), which shifts which phases start at i = 1.  Phases t < Z simply
+//     use i in [1, KP] instead of [0, KP): no multiplies by the structural zeros
+//     (config 4: 96 taps -> exactly 32 FFMA per output).
+//   * outputs go back through shared memory and one bulk store.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace scir_b200 {
 
-int launch_upfirdn_poly(scir_b200_ctx*, const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t,
-                        int64_t, float*, int64_t, int64_t, int64_t, bool* handled)
+namespace {
+
+constexpr int kPolyNT = 256;
+constexpr int kPolyMaxH = 1024;          // taps ride in the kernel parameters
+
+struct PolyTaps {
+    float c[kPolyMaxH];
+};
+
+struct PolyParams {
+    const float* x;
+    float* y;
+    long long ld_x, ld_y;
+    long long n_in;
+    long long m_begin, m_end;     // outputs [m_begin, m_end) land at y[row, m - m_begin]
+    long long base_m;             // first output of tile 0 (a multiple of 4*up: q0 is 16-B aligned)
+    long long ntiles;
+    int nchunk;
+    int in_vec_ok, out_vec_ok;
+};
+
+// UP/DOWN: rate; G: groups of `up` outputs per thread; KCP: taps per phase per chunk; Z: leading
+// zero taps; NCH: compile-time chunk count (0 = runtime loop, taps through LDCU).
+template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
+__global__ void __launch_bounds__(kPolyNT, 3)
+upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps)
+{
+    constexpr int NT = kPolyNT;
+    constexpr int R = UP * G;
+    constexpr int SIN = DOWN * G;
+    static_assert(SIN % 4 == 0 && (SIN / 4) % 2 == 1, "dense tile must be conflict-free for LDS.128");
+    static_assert(KCP % 4 == 0 && Z < UP, "chunk geometry");
+    constexpr int TILE_OUT = NT * R;
+    constexpr int TILE_IN = NT * SIN;
+    constexpr int ZP = (Z > 0) ? 4 : 0;
+    constexpr int DQMAX = ((R - 1) * DOWN) / UP;
+    constexpr int W4 = (KCP + ZP + DQMAX + 1 + 3) / 4;
+
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+
+    const int tid = threadIdx.x;
+    const int nchunk = (NCH > 0) ? NCH : q.nchunk;
+    const int HALO = nchunk * KCP + ZP;
+    const int len = HALO + TILE_IN + 4;
+    const long long bid = blockIdx.x;
+    const long long row = bid / q.ntiles;
+    const long long tile = bid - row * q.ntiles;
+    const long long m0 = q.base_m + tile * TILE_OUT;
+    const long long q0 = (m0 / UP) * DOWN;
+    const long long a = q0 - HALO;                        // first input sample staged
+    const float* __restrict__ xr = q.x + row * q.ld_x;
+    float* __restrict__ yr = q.y + row * q.ld_y;
+
+    const bool bulk_in = q.in_vec_ok && a >= 0 && a + len <= q.n_in;
+    if (bulk_in) {
+        const uint32_t bar = smem_u32(&mbar);
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(bar, static_cast<uint32_t>(len) * 4u);
+            bulk_copy_g2s(smem_u32(smem), xr + a, static_cast<uint32_t>(len) * 4u, bar);
+        }
+        __syncthreads();
+        mbar_wait(bar, 0);
+    } else {
+        for (int s = tid; s < len; s += NT) {
+            const long long xi = a + s;
+            smem[s] = (xi >= 0 && xi < q.n_in) ? xr[xi] : 0.f;      // mode='constant', cval 0
+        }
+        __syncthreads();
+    }
+
+    float acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0.f;
+
+    const float* wbase = smem + HALO + tid * SIN;          // sample q0_thread
+    auto chunk = [&](int c) {
+        // window: samples q0_thread - (c+1)*KCP - ZP + s, s in [0, 4*W4)
+        const float4* w = reinterpret_cast<const float4*>(wbase - (c + 1) * KCP - ZP);
+        const float* tc = taps.c + c * (KCP * UP);
+#pragma unroll
+        for (int v4 = 0; v4 < W4; ++v4) {
+            const float4 v = w[v4];
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = 4 * v4 + e;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int tj = (j * DOWN) % UP;
+                    const int dq = (j * DOWN) / UP;
+                    const int ot = (tj < Z) ? 1 : 0;
+                    const int il = dq + KCP + ZP - s - ot;          // chunk-local tap index of this sample
+                    if (il >= 0 && il < KCP) acc[j] = fmaf(tc[(il + ot) * UP + tj], xv[e], acc[j]);
+                }
+            }
+        }
+    };
+    if constexpr (NCH > 0) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) chunk(c);
+    } else {
+        for (int c = 0; c < nchunk; ++c) chunk(c);
+    }
+
+    __syncthreads();                                        // every warp is done reading the tile
+    float* so = smem + tid * R;
+    if constexpr (R % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 4)
+            *reinterpret_cast<float4*>(so + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    } else if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 2) *reinterpret_cast<float2*>(so + j) = make_float2(acc[j], acc[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) so[j] = acc[j];
+    }
+
+    const bool bulk_out = q.out_vec_ok && m0 >= q.m_begin && m0 + TILE_OUT <= q.m_end;
+    if (bulk_out) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_copy_s2g(yr + (m0 - q.m_begin), smem_u32(smem), TILE_OUT * 4u);
+            bulk_store_wait_read<0>();
+        }
+    } else {
+        __syncthreads();
+        for (int s = tid; s < TILE_OUT; s += NT) {
+            const long long m = m0 + s;
+            if (m >= q.m_begin && m < q.m_end) yr[m - q.m_begin] = smem[s];
+        }
+    }
+}
+
+template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
+int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid)
+{
+    constexpr int R = UP * G, SIN = DOWN * G;
+    const int halo = nchunk * KCP + ((Z > 0) ? 4 : 0);
+    const size_t floats = std::max<size_t>(static_cast<size_t>(halo) + kPolyNT * SIN + 4, static_cast<size_t>(kPolyNT) * R);
+    const size_t smem_bytes = floats * sizeof(float);
+    if (smem_bytes > static_cast<size_t>(ctx->max_smem_optin))
+        return set_error(SCIR_B200_ERR_UNSUPPORTED, "polyphase tile needs %zu B of shared memory", smem_bytes);
+    auto kern = upfirdn_tile_kernel<UP, DOWN, G, KCP, Z, NCH>;
+    static thread_local size_t configured[16] = {0};
+    if (smem_bytes > 48 * 1024 && configured[ctx->device & 15] < smem_bytes) {
+        SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)),
+                  "cudaFuncSetAttribute(upfirdn_tile_kernel)");
+        configured[ctx->device & 15] = smem_bytes;
+    }
+    kern<<<static_cast<unsigned>(grid), kPolyNT, smem_bytes, ctx->stream>>>(q, taps);
+    SCIR_CUDA(cudaGetLastError(), "upfirdn_tile_kernel launch");
+    ctx->launches++;
+    ctx->poly_launches++;
+    return SCIR_B200_OK;
+}
+
+// Z and NCH are runtime facts of the filter: dispatch onto the template grid.
+template <int UP, int DOWN, int G, int KCP, int Z>
+int launch_z(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid)
+{
+    if (nchunk == 1) return launch_one<UP, DOWN, G, KCP, Z, 1>(ctx, q, taps, nchunk, grid);
+    return launch_one<UP, DOWN, G, KCP, Z, 0>(ctx, q, taps, nchunk, grid);
+}
+
+template <int UP, int DOWN, int G, int KCP>
+int launch_rate(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, int z, long long grid)
+{
+    if constexpr (UP >= 2) {
+        if (z == 1) return launch_z<UP, DOWN, G, KCP, 1>(ctx, q, taps, nchunk, grid);
+    }
+    if constexpr (UP >= 3) {
+        if (z == 2) return launch_z<UP, DOWN, G, KCP, 2>(ctx, q, taps, nchunk, grid);
+    }
+    if constexpr (UP >= 4) {
+        if (z == 3) return launch_z<UP, DOWN, G, KCP, 3>(ctx, q, taps, nchunk, grid);
+    }
+    return launch_z<UP, DOWN, G, KCP, 0>(ctx, q, taps, nchunk, grid);
+}
+
+struct RateGeom {
+    int up, down, g;
+};
+// G per rate: (down*G) % 4 == 0 and (down*G/4) odd; R = up*G outputs per thread.
+constexpr RateGeom kRates[] = {
+    {3, 2, 10}, {2, 3, 12}, {2, 1, 12}, {1, 2, 10}, {3, 1, 4}, {1, 3, 12}, {4, 1, 4}, {1, 4, 5}, {4, 3, 4}, {3, 4, 5},
+};
+
+}  // namespace
+
+int launch_upfirdn_poly(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
+                        const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y, int64_t ld_y,
+                        int64_t m_begin, int64_t m_count, bool* handled)
 {
     *handled = false;
-    return SCIR_B200_OK;
+    constexpr int KCP = 32;
+    int g = 0;
+    for (const auto& r : kRates)
+        if (r.up == up && r.down == down) g = r.g;
+    if (g == 0) return SCIR_B200_OK;                                  // rate not in the template grid
+
+    // structural zeros at both ends of the filter (resample_poly's pre/post padding)
+    int64_t lo = 0, hi = len_h;
+    while (hi > 1 && h[hi - 1] == 0.f) --hi;
+    while (lo < hi - 1 && h[lo] == 0.f) ++lo;
+    const int z = (lo < up) ? static_cast<int>(lo) : 0;
+    int64_t kp = 1;                                                   // taps per phase after skipping
+    for (int64_t t = 0; t < up; ++t) {
+        if (hi - 1 - t < 0) continue;
+        const int64_t i_hi = (hi - 1 - t) / up;
+        const int64_t o_t = (t < z) ? 1 : 0;
+        kp = std::max<int64_t>(kp, i_hi - o_t + 1);
+    }
+    const int64_t nchunk = (kp + KCP - 1) / KCP;
+    if ((nchunk * KCP + 2) * up > kPolyMaxH) return SCIR_B200_OK;     // filter too long for the parameter block
+
+    thread_local PolyTaps* tl = nullptr;
+    if (!tl) tl = new PolyTaps();
+    for (int i = 0; i < kPolyMaxH; ++i) tl->c[i] = (i < hi) ? h[i] : 0.f;
+
+    PolyParams q{};
+    q.x = d_x; q.y = d_y; q.ld_x = ld_x; q.ld_y = ld_y; q.n_in = n_in;
+    q.m_begin = m_begin; q.m_end = m_begin + m_count;
+    const int64_t step = 4 * up;
+    q.base_m = (m_begin / step) * step;
+    const int64_t tile_out = static_cast<int64_t>(kPolyNT) * up * g;
+    q.ntiles = (q.m_end - q.base_m + tile_out - 1) / tile_out;
+    q.nchunk = static_cast<int>(nchunk);
+    const bool generic_io = (ctx->opt.upfirdn_variant == 2);
+    q.in_vec_ok = !generic_io && aligned16(d_x) && (ld_x % 4 == 0);
+    q.out_vec_ok = !generic_io && aligned16(d_y) && (ld_y % 4 == 0) && ((m_begin - q.base_m) % 4 == 0);
+    const long long grid = q.ntiles * batch;
+    if (grid > 0x7fffffffLL) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+
+    int rc = SCIR_B200_OK;
+#define SCIR_RATE(U, D, GG) \
+    if (up == U && down == D) { rc = launch_rate<U, D, GG, KCP>(ctx, q, *tl, q.nchunk, z, grid); *handled = (rc == SCIR_B200_OK); return rc; }
+    SCIR_RATE(3, 2, 10)
+    SCIR_RATE(2, 3, 12)
+    SCIR_RATE(2, 1, 12)
+    SCIR_RATE(1, 2, 10)
+    SCIR_RATE(3, 1, 4)
+    SCIR_RATE(1, 3, 12)
+    SCIR_RATE(4, 1, 4)
+    SCIR_RATE(1, 4, 5)
+    SCIR_RATE(4, 3, 4)
+    SCIR_RATE(3, 4, 5)
+#undef SCIR_RATE
+    return rc;
 }
 
 }  // namespace scir_b200

@@ -90,8 +90,16 @@ def lfilter(b, a, x, zi=None, *, ctx=None):
     y, yp, ldy = _alloc_like(dev, xo, batch, n)
     lib = _load()
     if zi is None:
-        _check(lib.scir_b200_lfilter_fir_f32(c.handle, _ptr(bt), bt.size, float(a[0]), xp, ld, None, None,
-                                             yp, ldy, batch, n))
+        if dev:
+            _check(lib.scir_b200_lfilter_fir_f32(c.handle, _ptr(bt), bt.size, float(a[0]), xp, ld, None, None,
+                                                 yp, ldy, batch, n))
+        else:
+            # host arrays: b / a[0] in f32 (_signaltools.py:2223), then the streaming *_host hot path
+            if float(a[0]) == 0.0:
+                raise ValueError("a[0] must be nonzero")
+            bs = (bt / np.float32(a[0])).astype(np.float32) if float(a[0]) != 1.0 else bt
+            _check(lib.scir_b200_fir1d_batched_f32_host(c.handle, xp, ld, _ptr(bs), bs.size, L.TAPS_LFILTER,
+                                                        yp, ldy, batch, n))
         return y[0] if was1d else y
     if not dev:
         km1 = bt.size - 1

@@ -136,9 +136,35 @@ def test_unaligned_and_strided_device_views():
     assert np.abs(out.cpu().numpy() - O.fir1d_batched_f32_acc64(big, taps)).max() <= tol(taps, big)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("k", [31, 63, 255, 700])
+def test_stream_kernel_many_tiles_per_cta(k):
+    """More tiles than resident CTAs (148 SMs x 3): every persistent CTA walks several tiles, both
+    pipeline stages wrap, edge tiles (non-bulk) interleave with bulk tiles.  Checked against the
+    independent naive kernel everywhere and against the oracle on a row subset."""
+    rng = np.random.RandomState(k)
+    batch, n = 96, 61000                                    # 12 tiles per row, 1152 tiles
+    x = (rng.rand(batch, n).astype(np.float32) * 2 - 1)
+    taps = rng.randn(k).astype(np.float32)
+    xd = dev(x)
+    y = gpu.fir1d_batched_f32_cuda(xd, taps)
+    naive = gpu.Context(0)
+    naive.set_option("variant", 2)
+    torch.cuda.synchronize()
+    y2 = gpu.fir1d_batched_f32_cuda(xd, taps, ctx=naive)
+    naive.sync()
+    assert float((y - y2).abs().max()) <= 2 * tol(taps, x)
+    rows = [0, 1, 47, 95]
+    want = O.fir1d_batched_f32_acc64(x[rows], taps)
+    assert np.abs(y.cpu().numpy()[rows] - want).max() <= tol(taps, x)
+    # twice in a row on the same ctx/stream: no state leaks between launches
+    y3 = gpu.fir1d_batched_f32_cuda(xd, taps)
+    assert torch.equal(y, y3)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_kernel_variants_agree(variant):
-    """variant 1 = tile kernel with generic (non-bulk) IO, 2 = naive 1-thread/output kernel."""
+    """variant 1 = streaming kernel with generic (non-bulk) IO, 2 = naive 1-thread/output kernel,
+    3 = one-tile-per-CTA kernel."""
     rng = np.random.RandomState(5)
     x = (rng.rand(3, 15000).astype(np.float32) * 2 - 1)
     taps = rng.randn(100).astype(np.float32)
@@ -292,6 +318,49 @@ def test_upfirdn_vs_oracle_random(up, down, len_h, n, batch):
     y1 = signal.upfirdn(h, xd, up, down, ctx=ctx)
     ctx.sync()
     assert np.abs(y1.cpu().numpy() - want).max() <= tol(h, x)
+
+
+RATES = [(3, 2), (2, 3), (2, 1), (1, 2), (3, 1), (1, 3), (4, 1), (1, 4), (4, 3), (3, 4)]
+
+
+@pytest.mark.parametrize("up,down", RATES)
+@pytest.mark.parametrize("lead,trail,len_h", [(0, 0, 33), (1, 0, 97), (2, 3, 64), (3, 1, 200), (5, 0, 31), (0, 0, 3)])
+def test_upfirdn_tile_kernel_rates(up, down, lead, trail, len_h):
+    """Every templated rate of the polyphase tile kernel x leading/trailing structural zeros
+    (resample_poly's padding) x 1..3 tap chunks, several tiles per row, vs the oracle; the generic
+    one-thread-per-output kernel and the non-bulk tile IO path must agree."""
+    rng = np.random.RandomState(up * 1000 + down * 100 + lead * 10 + len_h)
+    h = rng.randn(len_h).astype(np.float32)
+    h[:lead] = 0
+    if trail:
+        h[-trail:] = 0
+    n = 30011
+    x = (rng.rand(3, n).astype(np.float32) * 2 - 1)
+    want = O.upfirdn(h, x, up, down)
+    xd = dev(x)
+    y = signal.upfirdn(h, xd, up, down).cpu().numpy()
+    assert y.shape == want.shape
+    assert np.abs(y - want).max() <= tol(h, x)
+    for variant in (1, 2):
+        ctx = gpu.Context(0)
+        ctx.set_option("upfirdn_variant", variant)
+        torch.cuda.synchronize()
+        yv = signal.upfirdn(h, xd, up, down, ctx=ctx)
+        ctx.sync()
+        assert np.abs(yv.cpu().numpy() - want).max() <= tol(h, x)
+
+
+def test_upfirdn_tile_kernel_is_the_one_that_runs():
+    """The templated rates must be served by ONE tile-kernel launch (not the generic fallback)."""
+    rng = np.random.RandomState(1)
+    h = rng.randn(97).astype(np.float32)
+    xd = dev(rng.rand(4, 100000).astype(np.float32))
+    ctx = gpu.torch_context(xd)
+    n0, p0 = ctx.launch_count(), ctx.get_option("poly_launches")
+    signal.upfirdn(h, xd, 3, 2)
+    assert ctx.launch_count() == n0 + 1 and ctx.get_option("poly_launches") == p0 + 1
+    signal.upfirdn(h, xd, 160, 147)                         # not in the template grid: generic kernel
+    assert ctx.get_option("poly_launches") == p0 + 1
 
 
 def test_upfirdn_windowed_output():

@@ -1,0 +1,54 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, bench lines for the configs, ncu launch list + full captures.
+# Usage (from the repo root on the GPU box): bash tools/gpu_session.sh <tag> [stages...]
+#   stages: test smoke bench ref launches ncu_c2 ncu_c4 ncu_c5 ncu_c3 (default: all but ncu_c5/ncu_c3)
+TAG=${1:-r01}; shift
+STAGES=${*:-test smoke bench ref launches ncu_c2 ncu_c4}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/nvidia_smi.csv 2>&1
+python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || { echo BUILD FAILED; tail -30 $OUT/build.log; }
+if has test; then
+  timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+  tail -25 $OUT/pytest_gpu.log
+fi
+if has smoke; then
+  timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke.log
+fi
+if has bench; then
+  for cfg in ${BENCH_CFGS:-c2 c1 c4 c5 c3}; do
+    steps=20; [ $cfg = c3 ] && steps=5
+    extra=""; [ $cfg != c2 ] && extra="--no-cpu"
+    timeout 600 python bench.py --config $cfg --steps $steps --warmup 3 $extra > $OUT/bench_$cfg.json 2> $OUT/bench_$cfg.err; echo "bench $cfg rc=$?"
+    python - <<PY
+import json
+try:
+    d=json.load(open("$OUT/bench_$cfg.json"))
+    r=d["roofline"]
+    print("$cfg", "value=%.1f"%d["value"], "ms=%.3f"%d["ms_per_step"], "fp32_frac=%.3f"%r["fp32"]["frac_nominal"], "hbm_frac=%.3f"%r["frac"], "shape_frac=%.3f"%r["shape_roofline"]["frac"], "e2e=", (d.get("e2e") or {}).get("value"), "clk", d["clocks"])
+except Exception as e:
+    print("$cfg bench parse failed", e); print(open("$OUT/bench_$cfg.err").read()[-2000:])
+PY
+  done
+  for v in ${BENCH_VARIANTS:-3}; do
+    timeout 300 python bench.py --config c2 --steps 20 --warmup 3 --no-cpu --no-e2e --variant $v > $OUT/bench_c2_v$v.json 2> $OUT/bench_c2_v$v.err
+    python -c "import json; d=json.load(open('$OUT/bench_c2_v$v.json')); print('c2 variant $v', d['value'], d['ms_per_step'])"
+  done
+fi
+if has ref; then
+  timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json
+fi
+if has launches; then
+  # launch list of the default bench command (cold-cache, serialised: shares only)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c2.csv \
+     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+fi
+for cfg in c2 c4 c5 c3; do
+  if has ncu_$cfg; then
+    pat="regex:fir_|upfirdn_"
+    timeout 900 ncu --set full --clock-control none --import-source on -k "$pat" -s 3 -c 1 -f -o $OUT/prof_$cfg \
+       python bench.py --config $cfg --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_$cfg.log 2>&1; echo "ncu full $cfg rc=$?"
+  fi
+done
+ls -la $OUT
