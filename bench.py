@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="ctx option for A/B runs, e.g. long_tap_path=2 toeplitz_terms=3")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.rows:
@@ -258,6 +260,9 @@ def main():
     ctx = gpu.torch_context(x)
     if args.variant:
         ctx.set_option("variant", args.variant)
+    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
+    for key, val in opts.items():
+        ctx.set_option(key, val)
 
     def barrier():
         if world > 1:
@@ -319,6 +324,8 @@ def main():
             ay = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(rows, n))
             ax[:] = x.cpu().numpy()
             hctx = gpu.Context(local_rank)
+            for key, val in opts.items():
+                hctx.set_option(key, val)
             order = L.TAPS_SCIR if cfg["op"] == "fir" else L.TAPS_LFILTER
             e_steps = max(3, min(args.steps, 10))
             for _ in range(2):
@@ -364,7 +371,8 @@ def main():
                        "global_rows": rows * world, "sharding": f"rows x{world}, no collective",
                        "l2": "inputs larger than L2 (per-step working set >> 126 MB)" if abytes > 3e8 else
                              "working set fits L2 (latency/plumbing config)",
-                       "variant": args.variant},
+                       "variant": args.variant, "options": opts,
+                       "tensor_core_launches": ctx.get_option("toeplitz_launches")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

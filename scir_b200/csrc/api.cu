@@ -92,6 +92,16 @@ static int check_taps(const float* taps, int64_t k)
     return SCIR_B200_OK;
 }
 
+// Kernel choice for one FIR pass: the tcgen05 block-Toeplitz contraction for long filters (or when
+// forced), the FP32 direct family otherwise.
+int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
+{
+    const int64_t mode = ctx->opt.long_tap_path;
+    const bool want = (mode == 2) || (mode == 0 && k >= ctx->opt.toeplitz_min_k);
+    if (want && ctx->opt.variant == 0 && toeplitz_supported(ctx, pass, k)) return launch_fir_toeplitz(ctx, pass, c, k);
+    return launch_fir_pass(ctx, pass, c, k);
+}
+
 // One causal zero-state FIR over (batch, n): the reference hot path.
 static int fir_causal(scir_b200_ctx* ctx, const float* c, int64_t k, const float* d_x, int64_t ld_x,
                       float* d_y, int64_t ld_y, int64_t batch, int64_t n)
@@ -100,9 +110,7 @@ static int fir_causal(scir_b200_ctx* ctx, const float* c, int64_t k, const float
     p.x = d_x; p.y = d_y; p.ld_x = ld_x; p.ld_y = ld_y; p.batch = batch;
     p.n_x = n; p.n_v = n; p.in_off = 0; p.out_off = 0; p.out_begin = 0; p.out_end = n;
     p.ext_mode = EXT_NONE; p.bound = BOUND_ZERO; p.dir = +1;
-    if (k >= 1024 && ctx->opt.long_tap_path != 1 && toeplitz_supported(ctx, p, k))
-        return launch_fir_toeplitz(ctx, p, c, k);
-    return launch_fir_pass(ctx, p, c, k);
+    return launch_fir(ctx, p, c, k);
 }
 
 static int filtfilt_device(scir_b200_ctx* ctx, const float* b, int64_t k, int pad_mode, int64_t padlen,
@@ -137,13 +145,13 @@ static int filtfilt_device(scir_b200_ctx* ctx, const float* b, int64_t k, int pa
     f.x = d_x; f.ld_x = ld_x; f.y = y1; f.ld_y = ld1; f.batch = batch;
     f.n_x = n; f.n_v = n_v; f.in_off = -edge; f.out_off = padlead;
     f.out_begin = 0; f.out_end = n_v; f.ext_mode = ext; f.bound = bound; f.dir = +1;
-    SCIR_TRY(launch_fir_pass(ctx, f, b, k));
+    SCIR_TRY(launch_fir(ctx, f, b, k));
 
     FirPass r{};                                                  // backward, keep [edge, edge+n)
     r.x = y1; r.ld_x = ld1; r.y = d_y; r.ld_y = ld_y; r.batch = batch;
     r.n_x = n_v; r.n_v = n_v; r.in_off = padlead; r.out_off = -edge;
     r.out_begin = edge; r.out_end = edge + n; r.ext_mode = EXT_NONE; r.bound = bound; r.dir = -1;
-    return launch_fir_pass(ctx, r, b, k);
+    return launch_fir(ctx, r, b, k);
 }
 
 static int resample_plan(int64_t n_in, int64_t len_h, int64_t up, int64_t down, scir_b200_resample_plan* p)
@@ -369,6 +377,8 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "host_block_rows")) return &o.host_block_rows;
     if (!strcmp(key, "long_tap_path")) return &o.long_tap_path;
     if (!strcmp(key, "upfirdn_variant")) return &o.upfirdn_variant;
+    if (!strcmp(key, "toeplitz_terms")) return &o.toeplitz_terms;
+    if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     return nullptr;
 }
 
@@ -385,6 +395,10 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
 {
     SCIR_TRY(check_ctx(ctx));
     if (!value) return set_error(SCIR_B200_ERR_INVALID_ARG, "value is NULL");
+    if (key && !strcmp(key, "toeplitz_launches")) {                   // read-only statistic
+        *value = static_cast<int64_t>(ctx->toeplitz_launches);
+        return SCIR_B200_OK;
+    }
     if (key && !strcmp(key, "poly_launches")) {                       // read-only statistic
         *value = static_cast<int64_t>(ctx->poly_launches);
         return SCIR_B200_OK;

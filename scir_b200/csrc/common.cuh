@@ -34,7 +34,9 @@ void clear_error();
 struct Options {
     int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
     int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
-    int64_t long_tap_path = 0;  // 0 auto; 1 force FP32 direct; 2 force tcgen05 Toeplitz
+    int64_t long_tap_path = 0;  // 0 auto (tensor path for k >= toeplitz_min_k); 1 force FP32 direct; 2 force tcgen05 Toeplitz
+    int64_t toeplitz_terms = 4; // split-BF16 products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
+    int64_t toeplitz_min_k = 1024; // auto mode: smallest tap count routed to the tensor path
     int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
 };
 
@@ -52,6 +54,7 @@ struct scir_b200_ctx {
     int sm_count = 0;
     int max_smem_optin = 0;
     uint64_t launches = 0;
+    uint64_t toeplitz_launches = 0;        // launches served by the tcgen05 Toeplitz kernel
     uint64_t poly_launches = 0;            // launches served by the polyphase TILE kernel (tests)
     scir_b200::Options opt;
     scir_b200::DeviceBuffer scratch;       // filtfilt intermediate etc.
@@ -93,6 +96,9 @@ struct FirPass {
 };
 
 // c: coefficients by delay index (lfilter order), length k.
+// launch_fir picks the kernel (tcgen05 Toeplitz vs FP32 direct) from the ctx options; launch_fir_pass
+// is the FP32 direct family.
+int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 int launch_fir_pass(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 
 // lfilter streaming-state helpers (small kernels)

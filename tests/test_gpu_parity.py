@@ -136,17 +136,22 @@ def test_unaligned_and_strided_device_views():
     assert np.abs(out.cpu().numpy() - O.fir1d_batched_f32_acc64(big, taps)).max() <= tol(taps, big)
 
 
-@pytest.mark.parametrize("k", [31, 63, 255, 700])
-def test_stream_kernel_many_tiles_per_cta(k):
+@pytest.mark.parametrize("k,variant", [(31, 0), (63, 0), (255, 0), (700, 0), (63, 4), (255, 4), (63, 5), (255, 6),
+                                       (700, 6), (31, 3)])
+def test_stream_kernel_many_tiles_per_cta(k, variant):
     """More tiles than resident CTAs (148 SMs x 3): every persistent CTA walks several tiles, both
     pipeline stages wrap, edge tiles (non-bulk) interleave with bulk tiles.  Checked against the
     independent naive kernel everywhere and against the oracle on a row subset."""
     rng = np.random.RandomState(k)
-    batch, n = 96, 61000                                    # 12 tiles per row, 1152 tiles
+    batch, n = 96, 150000                                   # many tiles per warp / CTA
     x = (rng.rand(batch, n).astype(np.float32) * 2 - 1)
     taps = rng.randn(k).astype(np.float32)
     xd = dev(x)
-    y = gpu.fir1d_batched_f32_cuda(xd, taps)
+    main = gpu.Context(0)
+    main.set_option("variant", variant)
+    torch.cuda.synchronize()
+    y = gpu.fir1d_batched_f32_cuda(xd, taps, ctx=main)
+    main.sync()
     naive = gpu.Context(0)
     naive.set_option("variant", 2)
     torch.cuda.synchronize()
@@ -157,14 +162,15 @@ def test_stream_kernel_many_tiles_per_cta(k):
     want = O.fir1d_batched_f32_acc64(x[rows], taps)
     assert np.abs(y.cpu().numpy()[rows] - want).max() <= tol(taps, x)
     # twice in a row on the same ctx/stream: no state leaks between launches
-    y3 = gpu.fir1d_batched_f32_cuda(xd, taps)
+    y3 = gpu.fir1d_batched_f32_cuda(xd, taps, ctx=main)
+    main.sync()
     assert torch.equal(y, y3)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_kernel_variants_agree(variant):
-    """variant 1 = streaming kernel with generic (non-bulk) IO, 2 = naive 1-thread/output kernel,
-    3 = one-tile-per-CTA kernel."""
+    """variant 1 = generic (non-bulk) IO, 2 = naive 1-thread/output kernel, 3 = one-tile-per-CTA kernel,
+    4 = CTA-streaming kernel, 5/6 = warp-streaming kernel with 20/28 outputs per thread."""
     rng = np.random.RandomState(5)
     x = (rng.rand(3, 15000).astype(np.float32) * 2 - 1)
     taps = rng.randn(100).astype(np.float32)

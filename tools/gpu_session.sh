@@ -9,6 +9,10 @@ mkdir -p $OUT
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/nvidia_smi.csv 2>&1
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || { echo BUILD FAILED; tail -30 $OUT/build.log; }
+if has toep; then
+  timeout 600 python -m pytest tests/test_gpu_toeplitz.py -x -q -s > $OUT/pytest_toep.log 2>&1; echo "toeplitz pytest rc=$?" | tee -a $OUT/pytest_toep.log
+  tail -40 $OUT/pytest_toep.log
+fi
 if has test; then
   timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
   tail -25 $OUT/pytest_gpu.log
@@ -35,6 +39,20 @@ PY
     timeout 300 python bench.py --config c2 --steps 20 --warmup 3 --no-cpu --no-e2e --variant $v > $OUT/bench_c2_v$v.json 2> $OUT/bench_c2_v$v.err
     python -c "import json; d=json.load(open('$OUT/bench_c2_v$v.json')); print('c2 variant $v', d['value'], d['ms_per_step'])"
   done
+fi
+if has toepbench; then
+  for spec in "c3 toeplitz_terms=3" "c3 toeplitz_terms=4" "c5 long_tap_path=2 toeplitz_terms=3" "c5 long_tap_path=2 toeplitz_terms=4" \
+              "c2 long_tap_path=2 toeplitz_terms=3" "c2 long_tap_path=2 toeplitz_terms=4" "c2 long_tap_path=2 toeplitz_terms=6"; do
+    set -- $spec; cfg=$1; shift; o=""; tag=$cfg; for kv in "$@"; do o="$o --opt $kv"; tag="${tag}_${kv#*=}"; done
+    timeout 300 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu --no-e2e $o > $OUT/benchT_$tag.json 2> $OUT/benchT_$tag.err
+    python -c "import json; d=json.load(open('$OUT/benchT_$tag.json')); print('$spec ->', round(d['value'],2), 'Gs/s', round(d['ms_per_step'],3), 'ms', 'tc_launches', d['config'].get('tensor_core_launches'))" || tail -5 $OUT/benchT_$tag.err
+  done
+fi
+if has ncu_toep; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_toeplitz -s 3 -c 1 -f -o $OUT/prof_c3_toeplitz \
+     python bench.py --config c3 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_c3_toeplitz.log 2>&1; echo "ncu toeplitz c3 rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_toeplitz -s 3 -c 1 -f -o $OUT/prof_c2_toeplitz \
+     python bench.py --config c2 --opt long_tap_path=2 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_c2_toeplitz.log 2>&1; echo "ncu toeplitz c2 rc=$?"
 fi
 if has ref; then
   timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json
