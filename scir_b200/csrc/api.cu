@@ -379,6 +379,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "upfirdn_variant")) return &o.upfirdn_variant;
     if (!strcmp(key, "toeplitz_terms")) return &o.toeplitz_terms;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
+    if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
     return nullptr;
 }
 

@@ -36,6 +36,7 @@ struct Options {
     int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
     int64_t long_tap_path = 0;  // 0 auto (tensor path for k >= toeplitz_min_k); 1 force FP32 direct; 2 force tcgen05 Toeplitz
     int64_t toeplitz_terms = 4; // split-BF16 products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
+    int64_t toeplitz_loader = 0; // 0 auto (TMA ring when it fits); 1 force the register-prefetch loader
     int64_t toeplitz_min_k = 1024; // auto mode: smallest tap count routed to the tensor path
     int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
 };

@@ -20,10 +20,13 @@
 //       + mm (4 terms), + hl, lh (6 terms); FP32 accumulation in TMEM.  Worst case per product
 //       3 * 2^-18 (3 terms) / 2 * 2^-18 (4 terms) relative, against the path's 1e-5 tolerance.
 //
-// Warp roles (one persistent CTA per SM, 288 threads):
+// Warp roles (one persistent CTA per SM, 448 threads):
 //   warps 0-3  epilogue: tcgen05.ld their TMEM lane quarter, coalesced 128-B row stores to HBM
-//   warps 4-7  loader  : LDG.128 -> BF16 split in registers -> STS.128 into the slab (fence.proxy.async)
-//   warp  8    MMA     : one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M128 N128 K16)
+//   warps 4-11 loader  : LDG.128 of the NEXT tile into registers while the tensor core still reads the
+//                        slab, then BF16 split -> STS.128 (fence.proxy.async) as soon as the slab is free
+//   warp  12   MMA     : one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M128 N128 K16)
+//   warp  13   TMA     : short filters only (smem to spare): one lane prefetches whole fp32 tiles two
+//                        ahead with cp.async.bulk into a raw ring; warps 4-11 then convert smem -> smem
 // Pipelines: slab full/empty (loader <-> MMA, tcgen05.commit releases), accumulator full/empty
 // (MMA <-> epilogue, 2 x 128 TMEM columns), all on mbarriers.
 #include "common.cuh"
@@ -38,8 +41,9 @@ namespace {
 
 constexpr int TB = 128;                 // block length: MMA M, and the K extent of one p-block
 constexpr int TN = 128;                 // blocks (columns) per tile: MMA N
-constexpr int kEpiWarps = 4, kLoadWarps = 4;
-constexpr int kToepThreads = (kEpiWarps + kLoadWarps + 1) * 32;
+constexpr int kEpiWarps = 4, kLoadWarps = 8;
+constexpr int kMmaWarp = kEpiWarps + kLoadWarps, kTmaWarp = kMmaWarp + 1;
+constexpr int kToepThreads = (kEpiWarps + kLoadWarps + 2) * 32;
 constexpr int kTmemCols = 2 * TN;       // two accumulator stages
 
 struct ToepTaps {
@@ -49,6 +53,7 @@ struct ToepTaps {
 struct ToepParams {
     FirPass p;
     long long first_col;                // block index of tile 0's first output column
+    long long org;                      // block j covers causal indices [128 j - org, 128 j - org + 128): org in [0,3] makes 8-sample chunks 16-B aligned in memory
     long long ip_lo, ip_hi;             // outputs wanted, in the kernel's causal index i' (see map_index)
     long long fast_lo, fast_hi;         // virtual indices i whose sample is x[i + in_off] verbatim
     int fast_ok;                        // 16-byte alignment of 8-sample chunks holds on the fast path
@@ -59,6 +64,7 @@ struct ToepParams {
     int nver;                           // split terms kept per operand: 2 (hi, mid) or 3 (+ lo)
     int terms;                          // 3, 4 or 6 products
     int stages;                         // slab stages, 1 or 2
+    int raw_stages;                     // 2: fp32 tiles are prefetched by TMA bulk copies into a raw ring; 0: register prefetch
     int k;
     int hank_cores;                     // 16 * pmax + 31
 };
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(kToepThreads, 1)
 fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[8];    // slab_full[2] slab_empty[2] acc_full[2] acc_empty[2]
+    __shared__ __align__(8) unsigned long long bars[12];   // slab_full[2] slab_empty[2] acc_full[2] acc_empty[2] raw_full[2] raw_empty[2]
     __shared__ uint32_t tmem_base_holder;
 
     const FirPass& p = q.p;
@@ -184,7 +190,15 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     const uint32_t slab0 = smem0 + hank_bytes * static_cast<uint32_t>(q.nver);
     const uint32_t bar0 = smem_u32(&bars[0]);
     auto BAR = [&](int which, int idx) { return bar0 + 8u * static_cast<uint32_t>(which * 2 + idx); };
-    enum { SLAB_FULL = 0, SLAB_EMPTY = 1, ACC_FULL = 2, ACC_EMPTY = 3 };
+    enum { SLAB_FULL = 0, SLAB_EMPTY = 1, ACC_FULL = 2, ACC_EMPTY = 3, RAW_FULL = 4, RAW_EMPTY = 5 };
+    const uint32_t raw_bytes = static_cast<uint32_t>(TN + q.pmax) * TB * 4u;     // one fp32 tile incl. halo columns
+    const uint32_t raw0_off = (hank_bytes + static_cast<uint32_t>(q.stages) * ver_bytes) * static_cast<uint32_t>(q.nver);
+    // a tile whose N + P columns are plain, aligned memory can be fetched by one bulk copy
+    auto tile_lo = [&](long long ipA) { return (p.dir > 0) ? ipA : (p.n_v - ipA - static_cast<long long>(TN + q.pmax) * TB); };
+    auto tile_bulk = [&](long long ipA) {
+        const long long lo = tile_lo(ipA);
+        return q.fast_ok && lo >= q.fast_lo && lo + static_cast<long long>(TN + q.pmax) * TB <= q.fast_hi;
+    };
 
     // ---- one-time set-up: barriers, TMEM, the 8x-expanded (Hankel) tap arrays ------------------------------
     if (tid == 0) {
@@ -193,10 +207,12 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             mbar_init(BAR(SLAB_EMPTY, i), 1);
             mbar_init(BAR(ACC_FULL, i), 1);
             mbar_init(BAR(ACC_EMPTY, i), kEpiWarps * 32);
+            mbar_init(BAR(RAW_FULL, i), 1);
+            mbar_init(BAR(RAW_EMPTY, i), kLoadWarps * 32);
         }
         fence_mbar_init();
     }
-    if (warp == kEpiWarps + kLoadWarps) tmem_alloc(smem_u32(&tmem_base_holder), kTmemCols);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_holder), kTmemCols);
     {
         // H[u][i][e] = g[8u + i + e],  g[w] = c[128 P + 127 - w]  (zero outside [0, k))
         const int top = TB * q.pmax + (TB - 1);
@@ -220,50 +236,128 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     const uint32_t tmem_base = tmem_base_holder;
 
     const int ntiles = q.total_tiles;
-    if (warp >= kEpiWarps && warp < kEpiWarps + kLoadWarps) {
-        // ===== LOADER: stage the tile's N + P columns as split-BF16 core-matrix rows ======================
+    if (warp == kTmaWarp) {
+        // ===== TMA PRODUCER (short filters): whole fp32 tiles, two ahead, by cp.async.bulk ==================
+        if (q.raw_stages && lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int rs = it & 1;
+                mbar_wait(BAR(RAW_EMPTY, rs), ((it >> 1) & 1) ^ 1u);
+                const int row = t / q.tiles_per_row;
+                const int ct = t - row * q.tiles_per_row;
+                const long long ipA = (q.first_col + static_cast<long long>(ct) * TN - q.pmax) * TB - q.org;
+                if (tile_bulk(ipA)) {
+                    mbar_arrive_expect_tx(BAR(RAW_FULL, rs), raw_bytes);
+                    bulk_copy_g2s(smem0 + raw0_off + static_cast<uint32_t>(rs) * raw_bytes,
+                                  p.x + static_cast<long long>(row) * p.ld_x + tile_lo(ipA) + p.in_off, raw_bytes, BAR(RAW_FULL, rs));
+                } else {
+                    mbar_arrive(BAR(RAW_FULL, rs));        // edge tile: the converters synthesise it
+                }
+            }
+        }
+    } else if (warp >= kEpiWarps && warp < kEpiWarps + kLoadWarps && q.raw_stages) {
+        // ===== CONVERTER (short filters): raw fp32 tile in smem -> split-BF16 core-matrix rows ===============
         const int tl = tid - kEpiWarps * 32;
-        const int ncols = TN + q.pmax;
+        const int len = (TN + q.pmax) * TB;
+        const int nitems = (TN + q.pmax) * 16;
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int rs = it & 1;
             const int stage = (q.stages == 2) ? (it & 1) : 0;
             const uint32_t par = ((q.stages == 2) ? (it >> 1) : it) & 1;
-            mbar_wait(BAR(SLAB_EMPTY, stage), par ^ 1u);
             const int row = t / q.tiles_per_row;
             const int ct = t - row * q.tiles_per_row;
-            const long long j0 = q.first_col + static_cast<long long>(ct) * TN;
-            const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
+            const long long ipA = (q.first_col + static_cast<long long>(ct) * TN - q.pmax) * TB - q.org;
+            const bool bulk = tile_bulk(ipA);
+            float* raw = reinterpret_cast<float*>(smem_raw + raw0_off + static_cast<uint32_t>(rs) * raw_bytes);
+            mbar_wait(BAR(RAW_FULL, rs), (it >> 1) & 1);
+            if (!bulk) {                                   // zero / held / extended samples, causal order
+                const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
+                for (int i = tl; i < len; i += kLoadWarps * 32)
+                    raw[i] = tload(p, xr, (p.dir > 0) ? (ipA + i) : (p.n_v - 1 - (ipA + i)));
+                asm volatile("bar.sync 1, %0;" ::"n"(kLoadWarps * 32) : "memory");
+            }
+            mbar_wait(BAR(SLAB_EMPTY, stage), par ^ 1u);
             const uint32_t sbase = slab0 + static_cast<uint32_t>(stage) * stage_bytes;
-            for (int item = tl; item < ncols * 16; item += kLoadWarps * 32) {
+            const bool rev = bulk && p.dir < 0;            // bulk tiles of an anticausal pass sit in ascending memory order
+            for (int item = tl; item < nitems; item += kLoadWarps * 32) {
                 const int cidx = item >> 4, sc = item & 15;
-                const long long ip0 = (j0 - q.pmax + cidx) * TB + sc * 8;     // causal index of the chunk's first sample
+                const int o = cidx * TB + sc * 8;
+                const float* src = rev ? (raw + (len - 8 - o)) : (raw + o);
+                const float4 a = *reinterpret_cast<const float4*>(src);
+                const float4 b = *reinterpret_cast<const float4*>(src + 4);
                 float v[8];
-                if (p.dir > 0) {
-                    if (q.fast_ok && ip0 >= q.fast_lo && ip0 + 8 <= q.fast_hi) {
-                        const float4 a = *reinterpret_cast<const float4*>(xr + ip0 + p.in_off);
-                        const float4 b = *reinterpret_cast<const float4*>(xr + ip0 + p.in_off + 4);
-                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = tload(p, xr, ip0 + e);
-                    }
-                } else {
-                    const long long ihi = p.n_v - 1 - ip0;                  // sample e sits at virtual index ihi - e
-                    if (q.fast_ok && ihi - 7 >= q.fast_lo && ihi + 1 <= q.fast_hi) {
-                        const float4 a = *reinterpret_cast<const float4*>(xr + ihi - 7 + p.in_off);
-                        const float4 b = *reinterpret_cast<const float4*>(xr + ihi - 3 + p.in_off);
-                        v[7] = a.x; v[6] = a.y; v[5] = a.z; v[4] = a.w; v[3] = b.x; v[2] = b.y; v[1] = b.z; v[0] = b.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = tload(p, xr, ihi - e);
-                    }
-                }
+                v[0] = rev ? b.w : a.x; v[1] = rev ? b.z : a.y; v[2] = rev ? b.y : a.z; v[3] = rev ? b.x : a.w;
+                v[4] = rev ? a.w : b.x; v[5] = rev ? a.z : b.y; v[6] = rev ? a.y : b.z; v[7] = rev ? a.x : b.w;
                 split_store(v, q.nver, sbase + (static_cast<uint32_t>(sc) * q.slab_cols + cidx) * 16u, ver_bytes);
             }
             fence_proxy_async_smem();                      // my generic-proxy writes -> visible to the MMA's async reads
             mbar_arrive(BAR(SLAB_FULL, stage));
+            mbar_arrive(BAR(RAW_EMPTY, rs));               // raw[rs] may be overwritten by the next bulk copy
         }
-    } else if (warp == kEpiWarps + kLoadWarps) {
+    } else if (warp >= kEpiWarps && warp < kEpiWarps + kLoadWarps) {
+        // ===== LOADER (long filters): stage the tile's N + P columns as split-BF16 core-matrix rows ==========
+        // A thread owns items tl, tl + 256, ... (item = (column, 8-sample chunk)); its share of the NEXT
+        // tile is fetched into registers right after the current one is stored, so the HBM latency is
+        // spent while the tensor core works and only the convert + STS.128 phase waits on slab_empty.
+        constexpr int RMAX = ((TN + 32) * 16 + kLoadWarps * 32 - 1) / (kLoadWarps * 32);      // pmax <= 32 on this path
+        const int tl = tid - kEpiWarps * 32;
+        const int nitems = (TN + q.pmax) * 16;
+        float4 raw[RMAX][2];
+        uint32_t fastmask = 0;
+        auto fetch = [&](int t) {
+            const int row = t / q.tiles_per_row;
+            const int ct = t - row * q.tiles_per_row;
+            const long long j0 = q.first_col + static_cast<long long>(ct) * TN;
+            const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
+            fastmask = 0;
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int item = tl + r * (kLoadWarps * 32);
+                if (item < nitems) {
+                    const int cidx = item >> 4, sc = item & 15;
+                    const long long ip0 = (j0 - q.pmax + cidx) * TB + sc * 8 - q.org;   // causal index of the chunk's first sample
+                    // virtual index of the chunk's lowest address: ip0 (causal) or n_v-1-ip0-7 (anticausal)
+                    const long long lo = (p.dir > 0) ? ip0 : (p.n_v - 8 - ip0);
+                    if (q.fast_ok && lo >= q.fast_lo && lo + 8 <= q.fast_hi) {
+                        raw[r][0] = *reinterpret_cast<const float4*>(xr + lo + p.in_off);
+                        raw[r][1] = *reinterpret_cast<const float4*>(xr + lo + p.in_off + 4);
+                        fastmask |= 1u << r;
+                    } else {                                                   // edge chunk: causal order, rule by rule
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = tload(p, xr, (p.dir > 0) ? (ip0 + e) : (p.n_v - 1 - ip0 - e));
+                        raw[r][0] = make_float4(v[0], v[1], v[2], v[3]);
+                        raw[r][1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                }
+            }
+        };
+        int it = 0;
+        if (static_cast<int>(blockIdx.x) < ntiles) fetch(blockIdx.x);
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int stage = (q.stages == 2) ? (it & 1) : 0;
+            const uint32_t par = ((q.stages == 2) ? (it >> 1) : it) & 1;
+            mbar_wait(BAR(SLAB_EMPTY, stage), par ^ 1u);
+            const uint32_t sbase = slab0 + static_cast<uint32_t>(stage) * stage_bytes;
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int item = tl + r * (kLoadWarps * 32);
+                if (item < nitems) {
+                    const int cidx = item >> 4, sc = item & 15;
+                    const float4 a = raw[r][0], b = raw[r][1];
+                    const bool rev = (p.dir < 0) && ((fastmask >> r) & 1u);   // fast anticausal chunks were loaded ascending
+                    float v[8];
+                    v[0] = rev ? b.w : a.x; v[1] = rev ? b.z : a.y; v[2] = rev ? b.y : a.z; v[3] = rev ? b.x : a.w;
+                    v[4] = rev ? a.w : b.x; v[5] = rev ? a.z : b.y; v[6] = rev ? a.y : b.z; v[7] = rev ? a.x : b.w;
+                    split_store(v, q.nver, sbase + (static_cast<uint32_t>(sc) * q.slab_cols + cidx) * 16u, ver_bytes);
+                }
+            }
+            fence_proxy_async_smem();                      // my generic-proxy writes -> visible to the MMA's async reads
+            mbar_arrive(BAR(SLAB_FULL, stage));
+            if (t + static_cast<int>(gridDim.x) < ntiles) fetch(t + gridDim.x);
+        }
+    } else if (warp == kMmaWarp) {
         // ===== MMA ISSUER ===================================================================================
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -278,22 +372,26 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
                 const uint32_t sbase = slab0 + static_cast<uint32_t>(stage) * stage_bytes;
                 const uint32_t lbo_b = static_cast<uint32_t>(q.slab_cols) * 16u;
                 const uint32_t dcol = tmem_base + static_cast<uint32_t>(acc * TN);
+                // only the 14-bit start-address field changes between MMAs: add offsets in 16-byte units
+                const uint64_t a_h0 = smem_desc(smem0, 128u, 128u), x_h0 = smem_desc(sbase, lbo_b, 128u);
+                const uint64_t hank16 = hank_bytes >> 4, ver16 = ver_bytes >> 4;
+                const int terms = q.terms;
                 uint32_t accum = 0;
                 for (int pb = 0; pb <= q.pmax; ++pb) {
                     const int s_lo = max(0, TB * pb - (q.k - 1));       // first s with a non-zero tap in T_p
                     for (int ks = s_lo >> 4; ks < TB / 16; ++ks) {
-                        const uint32_t a_off = 128u * static_cast<uint32_t>(16 * (q.pmax - pb) + 2 * ks);
-                        const uint32_t b_off = static_cast<uint32_t>(2 * ks) * lbo_b + static_cast<uint32_t>(q.pmax - pb) * 16u;
-                        // (A version, X version): hh, hm, mh | mm | hl, lh
-                        const int na = q.terms;
-                        for (int term = 0; term < na; ++term) {
-                            const int va = (term == 0 || term == 1 || term == 4) ? 0 : ((term == 2 || term == 3) ? 1 : 2);
-                            const int vx = (term == 0 || term == 2 || term == 5) ? 0 : ((term == 1 || term == 3) ? 1 : 2);
-                            const uint64_t ad = smem_desc(smem0 + static_cast<uint32_t>(va) * hank_bytes + a_off, 128u, 128u);
-                            const uint64_t bd = smem_desc(sbase + static_cast<uint32_t>(vx) * ver_bytes + b_off, lbo_b, 128u);
-                            tc_mma_bf16(dcol, ad, bd, kIdesc, accum);
-                            accum = 1;
+                        const uint64_t a_h = a_h0 + static_cast<uint64_t>(8 * (16 * (q.pmax - pb) + 2 * ks));
+                        const uint64_t x_h = x_h0 + static_cast<uint64_t>(2 * ks * q.slab_cols + (q.pmax - pb));
+                        const uint64_t a_m = a_h + hank16, x_m = x_h + ver16;
+                        tc_mma_bf16(dcol, a_h, x_h, kIdesc, accum);     // hi * hi
+                        tc_mma_bf16(dcol, a_h, x_m, kIdesc, 1u);        // hi * mid
+                        tc_mma_bf16(dcol, a_m, x_h, kIdesc, 1u);        // mid * hi
+                        if (terms >= 4) tc_mma_bf16(dcol, a_m, x_m, kIdesc, 1u);
+                        if (terms == 6) {
+                            tc_mma_bf16(dcol, a_h, x_m + ver16, kIdesc, 1u);     // hi * lo
+                            tc_mma_bf16(dcol, a_m + hank16, x_h, kIdesc, 1u);    // lo * hi
                         }
+                        accum = 1;
                     }
                 }
                 tc_commit(BAR(SLAB_EMPTY, stage));         // slab may be refilled once these MMAs retire
@@ -314,15 +412,28 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
             mbar_wait(BAR(ACC_FULL, acc), apar);
             tc_fence_after();
+            const long long ip_first = j0 * TB - q.org, ip_last = (j0 + TN) * TB - q.org;      // this tile's outputs [first, last)
+            const bool interior = ip_first >= q.ip_lo && ip_last <= q.ip_hi;
 #pragma unroll 1
             for (int c4 = 0; c4 < TN / 32; ++c4) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * TN + c4 * 32), v);
-                const long long ipb = (j0 + c4 * 32) * TB + rr;
+                const long long ipb = (j0 + c4 * 32) * TB + rr - q.org;
+                if (interior) {                            // one base pointer, immediate offsets, no guards
+                    float* yb = yr + map_index(p, ipb);
+                    if (p.dir > 0) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const long long ip = ipb + static_cast<long long>(c) * TB;
-                    if (ip >= q.ip_lo && ip < q.ip_hi) yr[map_index(p, ip)] = __uint_as_float(v[c]);
+                        for (int c = 0; c < 32; ++c) yb[c * TB] = __uint_as_float(v[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) yb[-c * TB] = __uint_as_float(v[c]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const long long ip = ipb + static_cast<long long>(c) * TB;
+                        if (ip >= q.ip_lo && ip < q.ip_hi) yr[map_index(p, ip)] = __uint_as_float(v[c]);
+                    }
                 }
             }
             tc_fence_before();
@@ -332,7 +443,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kEpiWarps + kLoadWarps) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -350,6 +461,7 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, ToepPla
     q.p = pass;
     q.k = static_cast<int>(k);
     q.pmax = static_cast<int>((k - 1 + (TB - 1)) / TB);
+    if (q.pmax > 32) return false;                         // loader register budget (RMAX) and shared memory
     q.hank_cores = 16 * q.pmax + 31;
     q.slab_cols = (TN + q.pmax) | 1;
     int64_t terms = ctx->opt.toeplitz_terms;
@@ -360,14 +472,26 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, ToepPla
     const size_t stage = static_cast<size_t>(16) * q.slab_cols * 16 * q.nver;
     const size_t budget = static_cast<size_t>(ctx->max_smem_optin) - 1024;        // static smem + slack
     if (hank + stage > budget) return false;
-    q.stages = (hank + 2 * stage <= budget) ? 2 : 1;
+    const size_t raw = static_cast<size_t>(TN + q.pmax) * TB * 4;
+    if (ctx->opt.toeplitz_loader != 1 && hank + stage + 2 * raw <= budget) {
+        q.raw_stages = 2;                                  // short filters: TMA-prefetched fp32 ring + converter warps
+        q.stages = (hank + 2 * stage + 2 * raw <= budget) ? 2 : 1;
+    } else {
+        q.raw_stages = 0;                                  // long filters: register prefetch (no smem left for a ring)
+        q.stages = (hank + 2 * stage <= budget) ? 2 : 1;
+    }
     // outputs wanted, in causal index space i'
     q.ip_lo = (pass.dir > 0) ? pass.out_begin : (pass.n_v - pass.out_end);
     q.ip_hi = (pass.dir > 0) ? pass.out_end : (pass.n_v - pass.out_begin);
+    // origin shift: chunk addresses are (ip0 + in_off) causal, (n_v - 8 - ip0 + in_off) anticausal, ip0 = 8m - org
+    {
+        const long long al0 = (pass.dir > 0) ? pass.in_off : -(pass.n_v + pass.in_off);
+        q.org = ((al0 % 4) + 4) % 4;
+    }
     const long long tile_len = static_cast<long long>(TB) * TN;
-    const long long first_tile = q.ip_lo / tile_len;
+    const long long first_tile = (q.ip_lo + q.org) / tile_len;          // ip + org >= 0 is the block-grid coordinate
     q.first_col = first_tile * TN;
-    const long long tiles = (q.ip_hi + tile_len - 1) / tile_len - first_tile;
+    const long long tiles = (q.ip_hi + q.org + tile_len - 1) / tile_len - first_tile;
     if (tiles <= 0 || tiles * pass.batch > 0x7fffffffLL) return false;
     q.tiles_per_row = static_cast<int>(tiles);
     q.total_tiles = static_cast<int>(tiles * pass.batch);
@@ -377,10 +501,9 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, ToepPla
         q.fast_lo = std::max<long long>(q.fast_lo, -pass.in_off);
         q.fast_hi = std::min<long long>(q.fast_hi, pass.n_x - pass.in_off);
     }
-    const long long al = (pass.dir > 0) ? pass.in_off : (pass.n_v + pass.in_off);
-    q.fast_ok = aligned16(pass.x) && (pass.ld_x % 4 == 0) && (((al % 4) + 4) % 4 == 0);
+    q.fast_ok = aligned16(pass.x) && (pass.ld_x % 4 == 0);
     out->q = q;
-    out->smem_bytes = hank + static_cast<size_t>(q.stages) * stage;
+    out->smem_bytes = hank + static_cast<size_t>(q.stages) * stage + static_cast<size_t>(q.raw_stages) * raw;
     return true;
 }
 

@@ -22,10 +22,11 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def toep_ctx(terms=4):
+def toep_ctx(terms=4, loader=0):
     ctx = gpu.Context(0)
     ctx.set_option("long_tap_path", 2)
     ctx.set_option("toeplitz_terms", terms)
+    ctx.set_option("toeplitz_loader", loader)      # 0: TMA raw ring when it fits, 1: register-prefetch loader
     return ctx
 
 
@@ -38,15 +39,15 @@ def run(ctx, fn):
 
 @pytest.mark.parametrize("batch,n,k", [(1, 16384, 1), (2, 16384, 63), (2, 20000, 63), (3, 40000, 255), (2, 33000, 129),
                                        (1, 100000, 1500), (2, 70000, 4097), (1, 5, 3), (2, 127, 200), (5, 16385, 64)])
-@pytest.mark.parametrize("terms", [3, 4, 6])
-def test_toeplitz_fir_vs_oracle(batch, n, k, terms):
+@pytest.mark.parametrize("terms,loader", [(3, 0), (4, 0), (6, 0), (4, 1)])
+def test_toeplitz_fir_vs_oracle(batch, n, k, terms, loader):
     if terms == 6 and k > 1500:
         pytest.skip("three split terms per operand do not fit shared memory for very long filters")
     rng = np.random.RandomState(batch * 131 + n + k)
     x = (rng.rand(batch, n).astype(np.float32) * 2 - 1)
     taps = rng.randn(k).astype(np.float32)
     want = O.fir1d_batched_f32_acc64(x, taps)
-    ctx = toep_ctx(terms)
+    ctx = toep_ctx(terms, loader)
     t0 = ctx.get_option("toeplitz_launches")
     y = run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=ctx)).cpu().numpy()
     assert ctx.get_option("toeplitz_launches") == t0 + 1          # the tensor-core kernel is the one that ran
@@ -76,8 +77,9 @@ def test_toeplitz_error_budget_reported():
     print("\n".join(f"k={k} {name} terms={t}: {f:.3f} of tolerance" for k, name, t, f in rows))
 
 
+@pytest.mark.parametrize("loader", [0, 1])
 @pytest.mark.parametrize("padtype", ["odd", "even", "constant", None])
-def test_toeplitz_filtfilt_matches_direct_and_oracle(padtype):
+def test_toeplitz_filtfilt_matches_direct_and_oracle(padtype, loader):
     """Anticausal pass, held boundary and signal extension go through the Toeplitz loader too."""
     from scipy.signal import firwin
     rng = np.random.RandomState(11)
@@ -85,7 +87,7 @@ def test_toeplitz_filtfilt_matches_direct_and_oracle(padtype):
     x = (rng.rand(3, 40001).astype(np.float32) * 2 - 1)
     want = O.filtfilt_fir(b, x, padtype={"odd": O.PAD_ODD, "even": O.PAD_EVEN, "constant": O.PAD_CONSTANT,
                                          None: O.PAD_NONE}[padtype])
-    ctx = toep_ctx(4)
+    ctx = toep_ctx(4, loader)
     y = run(ctx, lambda: signal.filtfilt(b, [1.0], dev(x), padtype=padtype, ctx=ctx)).cpu().numpy()
     assert ctx.get_option("toeplitz_launches") == 2
     hc = np.convolve(b.astype(np.float64), b[::-1].astype(np.float64))
@@ -100,7 +102,11 @@ def test_toeplitz_many_tiles_and_views():
     taps = rng.randn(300).astype(np.float32)
     big = (rng.rand(40, 100003).astype(np.float32) * 2 - 1)
     xb = dev(big)
-    ctx = toep_ctx(4)
+    _many_tiles(taps, big, xb, toep_ctx(4, 0))
+    _many_tiles(taps, big, xb, toep_ctx(4, 1))
+
+
+def _many_tiles(taps, big, xb, ctx):
     naive = gpu.Context(0)
     naive.set_option("variant", 2)
     for view in (xb[:, :98304], xb[:, 1:], xb[::3, 3:90001]):
