@@ -378,6 +378,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "long_tap_path")) return &o.long_tap_path;
     if (!strcmp(key, "upfirdn_variant")) return &o.upfirdn_variant;
     if (!strcmp(key, "toeplitz_terms")) return &o.toeplitz_terms;
+    if (!strcmp(key, "toeplitz_split")) return &o.toeplitz_split;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
     return nullptr;

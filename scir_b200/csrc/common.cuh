@@ -35,8 +35,9 @@ struct Options {
     int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
     int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
     int64_t long_tap_path = 0;  // 0 auto (tensor path for k >= toeplitz_min_k); 1 force FP32 direct; 2 force tcgen05 Toeplitz
-    int64_t toeplitz_terms = 4; // split-BF16 products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
-    int64_t toeplitz_loader = 0; // 0 auto (TMA ring when it fits); 1 force the register-prefetch loader
+    int64_t toeplitz_terms = 3; // split products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
+    int64_t toeplitz_split = 0; // operand format of the split: 0 block-scaled FP16 (11-bit terms), 1 BF16 (8-bit terms)
+    int64_t toeplitz_loader = 0; // 0 auto (TMA-fed in-place buffers when they fit); 1 force the register-prefetch loader
     int64_t toeplitz_min_k = 1024; // auto mode: smallest tap count routed to the tensor path
     int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
 };

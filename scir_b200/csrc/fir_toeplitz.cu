@@ -16,24 +16,38 @@
 //       Setting the descriptor's leading AND stride byte offsets to 128 B makes every core matrix
 //       of every T_p alias into ONE 8x-expanded tap array H[u][i][e] = g[8u + i + e]
 //       ((16 P + 31) * 128 B per split term): no per-block A traffic at all.
-//   precision = split-BF16: x = xh + xm (+ xl), c = ch + cm (+ cl), products hh, hm, mh (3 terms),
-//       + mm (4 terms), + hl, lh (6 terms); FP32 accumulation in TMEM.  Worst case per product
-//       3 * 2^-18 (3 terms) / 2 * 2^-18 (4 terms) relative, against the path's 1e-5 tolerance.
+//   precision = split 16-bit operands, FP32 accumulation in TMEM.  Two formats:
+//       fmt 0 (default) FP16, block-scaled: every slab (tile + halo) is multiplied by a power of two
+//           that puts its max |x| in [2^14, 2^15), the taps likewise (once); x' = xh + xm, c' = ch + cm
+//           with 11-bit significands, products hh + hm + mh; what is dropped (mm and the two
+//           third-order residuals) is <= 3 * 2^-22 per product relative to max|x| * |c| -- an ABSOLUTE
+//           bound in exactly the unit of the path's tolerance (1e-5 * sum|h| * max|x|).  The scale is
+//           undone (exactly) in the epilogue.
+//       fmt 1 BF16 (8-bit significands): 3 / 4 / 6 products (hh, hm, mh, + mm, + hl, lh); kept for A/B.
 //
 // Warp roles (one persistent CTA per SM, 448 threads):
-//   warps 0-3  epilogue: tcgen05.ld their TMEM lane quarter, coalesced 128-B row stores to HBM
-//   warps 4-11 loader  : LDG.128 of the NEXT tile into registers while the tensor core still reads the
-//                        slab, then BF16 split -> STS.128 (fence.proxy.async) as soon as the slab is free
+//   warps 0-3  epilogue: tcgen05.ld their TMEM lane quarter, un-scale, coalesced 128-B row stores to HBM
+//   warps 4-11 loader / converter (256 threads)
 //   warp  12   MMA     : one elected lane issues tcgen05.mma (cta_group::1, kind::f16, M128 N128 K16)
-//   warp  13   TMA     : short filters only (smem to spare): one lane prefetches whole fp32 tiles two
-//                        ahead with cp.async.bulk into a raw ring; warps 4-11 then convert smem -> smem
-// Pipelines: slab full/empty (loader <-> MMA, tcgen05.commit releases), accumulator full/empty
-// (MMA <-> epilogue, 2 x 128 TMEM columns), all on mbarriers.
+//   warp  13   TMA     : in-place mode only: one lane prefetches whole fp32 tiles with cp.async.bulk
+// Two staging modes:
+//   IN-PLACE (K <= 385): three unified 66 KB buffers.  A buffer is filled with the raw fp32 tile by ONE
+//       bulk copy (tile t+2 is in flight while tile t+1 is converted and tile t is multiplied), the
+//       converter warps pull it into registers, meet at a named barrier (which also carries the
+//       max-|x| reduction), and write the split 16-bit slab back INTO THE SAME buffer; the MMA's
+//       tcgen05.commit hands the buffer back to the TMA warp.
+//   REGISTER (long filters; the Hankel arrays leave room for one or two slabs only): LDG.128 of the
+//       NEXT tile into registers while the tensor core still reads the slab, convert + STS.128 as soon
+//       as tcgen05.commit frees it.
+// Pipelines: buffer raw-full / slab-full / empty, accumulator full / empty (2 x 128 TMEM columns), all
+// on mbarriers.
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace scir_b200 {
 
@@ -42,9 +56,16 @@ namespace {
 constexpr int TB = 128;                 // block length: MMA M, and the K extent of one p-block
 constexpr int TN = 128;                 // blocks (columns) per tile: MMA N
 constexpr int kEpiWarps = 4, kLoadWarps = 8;
+constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMmaWarp = kEpiWarps + kLoadWarps, kTmaWarp = kMmaWarp + 1;
 constexpr int kToepThreads = (kEpiWarps + kLoadWarps + 2) * 32;
 constexpr int kTmemCols = 2 * TN;       // two accumulator stages
+constexpr int kMaxBuf = 3;
+constexpr int kPmaxLimit = 32;
+constexpr int RMAX = ((TN + kPmaxLimit) * 16 + kLoadThreads - 1) / kLoadThreads;   // items (8 samples) per loader thread
+
+enum { MODE_REGISTER = 0, MODE_INPLACE = 1 };
+enum { FMT_F16_SCALED = 0, FMT_BF16 = 1 };
 
 struct ToepTaps {
     float c[SCIR_B200_MAX_TAPS];        // by delay index, zero padded
@@ -63,10 +84,13 @@ struct ToepParams {
     int slab_cols;                      // odd, >= TN + pmax
     int nver;                           // split terms kept per operand: 2 (hi, mid) or 3 (+ lo)
     int terms;                          // 3, 4 or 6 products
-    int stages;                         // slab stages, 1 or 2
-    int raw_stages;                     // 2: fp32 tiles are prefetched by TMA bulk copies into a raw ring; 0: register prefetch
+    int mode;                           // MODE_REGISTER / MODE_INPLACE
+    int nbuf;                           // slab buffers: 3 in place, 1 or 2 in register mode
+    int fmt;                            // FMT_F16_SCALED / FMT_BF16
     int k;
     int hank_cores;                     // 16 * pmax + 31
+    unsigned buf_bytes;                 // one buffer (multiple of 128)
+    float tap_scale, tap_inv;           // power of two applied to the taps (fmt 0) and its inverse
 };
 
 // ---- tcgen05 / TMEM PTX ----------------------------------------------------------------------------------
@@ -85,13 +109,34 @@ __device__ __forceinline__ void tc_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Shared-memory matrix descriptors, SWIZZLE_NONE, K-major: 8 rows x 16 B core matrices.  Bits: [0,14)
+// addr>>4, [16,30) leading byte offset>>4 (between the two 16-B K chunks of one K=16 MMA), [32,46) stride
+// byte offset>>4 (between 8-row groups in M/N), [46,48) version = 1.  Only the low word changes between
+// MMAs (start address), so the issue loop does 32-bit adds and the 64-bit value is assembled in PTX.
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);           // SBO = 128 B for both operands
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo)
+{
+    return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -109,18 +154,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor, SWIZZLE_NONE, K-major: 8 rows x 16 B core matrices; `sbo` = byte
-// stride between 8-row groups (M/N direction), `lbo` = byte stride between the two 16-B K chunks of
-// one K=16 MMA.  Bits: [0,14) addr>>4, [16,30) lbo>>4, [32,46) sbo>>4, [46,48) version = 1.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+// kind::f16 instruction descriptor: D = F32 (bit 4), A/B format at bits 7 / 10 (0 = F16, 1 = BF16), both
+// K-major, N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int fmt)
 {
-    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
-           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+    const uint32_t ab = (fmt == FMT_BF16) ? 1u : 0u;
+    return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(TN >> 3) << 17) | (static_cast<uint32_t>(TB >> 4) << 24);
 }
-
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = TN.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(TN >> 3) << 17) |
-                            (static_cast<uint32_t>(TB >> 4) << 24);
 
 // ---- virtual input sequence (same rules as fir_direct.cu: zero / held boundary, odd / even / const ext) ----
 __device__ __forceinline__ float tload(const FirPass& p, const float* __restrict__ xr, long long i)
@@ -155,18 +195,35 @@ __device__ __forceinline__ long long map_index(const FirPass& p, long long ip)
     return (p.dir > 0) ? ip : (p.n_v - 1 - ip);
 }
 
-__device__ __forceinline__ void split_store(const float (&v)[8], int nver, uint32_t dst, uint32_t ver_bytes)
+// 8 consecutive samples -> one 16-byte core-matrix row per split term (hi | mid | lo), 16-bit each.
+template <bool F16>
+__device__ __forceinline__ void split_store(const float4& a, const float4& b, bool rev, float scale, int nver, uint32_t dst,
+                                            uint32_t ver_bytes)
 {
+    float v[8];
+    v[0] = rev ? b.w : a.x; v[1] = rev ? b.z : a.y; v[2] = rev ? b.y : a.z; v[3] = rev ? b.x : a.w;
+    v[4] = rev ? a.w : b.x; v[5] = rev ? a.z : b.y; v[6] = rev ? a.y : b.z; v[7] = rev ? a.x : b.w;
     uint32_t hi[4], mid[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-        const float r0 = v[2 * e] - __low2float(h), r1 = v[2 * e + 1] - __high2float(h);
-        const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
-        const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
-        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-        mid[e] = *reinterpret_cast<const uint32_t*>(&m);
-        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        if constexpr (F16) {
+            const float s0 = v[2 * e] * scale, s1 = v[2 * e + 1] * scale;
+            const __half2 h = __floats2half2_rn(s0, s1);
+            const float r0 = s0 - __low2float(h), r1 = s1 - __high2float(h);
+            const __half2 m = __floats2half2_rn(r0, r1);
+            const __half2 l = __floats2half2_rn(r0 - __low2float(m), r1 - __high2float(m));
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            mid[e] = *reinterpret_cast<const uint32_t*>(&m);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        } else {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            const float r0 = v[2 * e] - __low2float(h), r1 = v[2 * e + 1] - __high2float(h);
+            const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            mid[e] = *reinterpret_cast<const uint32_t*>(&m);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        }
     }
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ver_bytes), "r"(mid[0]), "r"(mid[1]), "r"(mid[2]), "r"(mid[3]) : "memory");
@@ -174,41 +231,87 @@ __device__ __forceinline__ void split_store(const float (&v)[8], int nver, uint3
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * ver_bytes), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
 }
 
+__device__ __forceinline__ uint32_t absmax_bits(const float4& a, const float4& b)
+{
+    const uint32_t m0 = max(__float_as_uint(a.x) & 0x7fffffffu, __float_as_uint(a.y) & 0x7fffffffu);
+    const uint32_t m1 = max(__float_as_uint(a.z) & 0x7fffffffu, __float_as_uint(a.w) & 0x7fffffffu);
+    const uint32_t m2 = max(__float_as_uint(b.x) & 0x7fffffffu, __float_as_uint(b.y) & 0x7fffffffu);
+    const uint32_t m3 = max(__float_as_uint(b.z) & 0x7fffffffu, __float_as_uint(b.w) & 0x7fffffffu);
+    return max(max(m0, m1), max(m2, m3));
+}
+
+// MMA issue for one tile: all P+1 Toeplitz blocks, every K=16 step that meets a non-zero tap, TERMS split
+// products each.  Run by the whole MMA warp with warp-uniform values; only the elected lane issues.
+template <int TERMS>
+__device__ __forceinline__ void issue_tile(const ToepParams& q, bool leader, uint32_t dcol, uint32_t a_lo0, uint32_t x_lo0,
+                                           uint32_t hank16, uint32_t ver16, uint32_t idesc)
+{
+    uint32_t accum = 0;
+    const uint32_t two_cols = 2u * static_cast<uint32_t>(q.slab_cols);
+    for (int pb = 0; pb <= q.pmax; ++pb) {
+        const int ks0 = max(0, TB * pb - (q.k - 1)) >> 4;                // first K step with a non-zero tap in T_p
+        uint32_t a = a_lo0 + 8u * static_cast<uint32_t>(16 * (q.pmax - pb) + 2 * ks0);
+        uint32_t x = x_lo0 + static_cast<uint32_t>(ks0) * two_cols + static_cast<uint32_t>(q.pmax - pb);
+        for (int ks = ks0; ks < TB / 16; ++ks) {
+            if (leader) {
+                tc_mma(dcol, a, x, idesc, accum);                        // hi * hi
+                tc_mma(dcol, a, x + ver16, idesc, 1u);                   // hi * mid
+                tc_mma(dcol, a + hank16, x, idesc, 1u);                  // mid * hi
+                if constexpr (TERMS >= 4) tc_mma(dcol, a + hank16, x + ver16, idesc, 1u);
+                if constexpr (TERMS == 6) {
+                    tc_mma(dcol, a, x + 2u * ver16, idesc, 1u);          // hi * lo
+                    tc_mma(dcol, a + 2u * hank16, x, idesc, 1u);         // lo * hi
+                }
+            }
+            accum = 1u;
+            a += 16u;
+            x += two_cols;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kToepThreads, 1)
 fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[12];   // slab_full[2] slab_empty[2] acc_full[2] acc_empty[2] raw_full[2] raw_empty[2]
+    // raw_full[3] slab_full[3] buf_empty[3] acc_full[2] acc_empty[2]
+    __shared__ __align__(8) unsigned long long bars[3 * kMaxBuf + 4];
     __shared__ uint32_t tmem_base_holder;
+    __shared__ uint32_t red_slots[2][kLoadWarps];          // per-warp max|x| bits, double-buffered by tile parity
+    __shared__ float inv_scale_ring[8];                    // loader -> epilogue: 1 / slab scale of tile it & 7 (a loader can be
+                                                           // at most 4 tiles ahead of the epilogue: see the barrier chain)
 
     const FirPass& p = q.p;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                      // warp-uniform for the compiler too
     const uint32_t smem0 = smem_u32(smem_raw);
     const uint32_t hank_bytes = static_cast<uint32_t>(q.hank_cores) * 128u;      // per version
     const uint32_t ver_bytes = 16u * static_cast<uint32_t>(q.slab_cols) * 16u;    // slab bytes per version
-    const uint32_t stage_bytes = ver_bytes * static_cast<uint32_t>(q.nver);
-    const uint32_t slab0 = smem0 + hank_bytes * static_cast<uint32_t>(q.nver);
+    const uint32_t buf0_off = hank_bytes * static_cast<uint32_t>(q.nver);
     const uint32_t bar0 = smem_u32(&bars[0]);
-    auto BAR = [&](int which, int idx) { return bar0 + 8u * static_cast<uint32_t>(which * 2 + idx); };
-    enum { SLAB_FULL = 0, SLAB_EMPTY = 1, ACC_FULL = 2, ACC_EMPTY = 3, RAW_FULL = 4, RAW_EMPTY = 5 };
-    const uint32_t raw_bytes = static_cast<uint32_t>(TN + q.pmax) * TB * 4u;     // one fp32 tile incl. halo columns
-    const uint32_t raw0_off = (hank_bytes + static_cast<uint32_t>(q.stages) * ver_bytes) * static_cast<uint32_t>(q.nver);
+    enum { RAW_FULL = 0, SLAB_FULL = kMaxBuf, BUF_EMPTY = 2 * kMaxBuf, ACC_FULL = 3 * kMaxBuf, ACC_EMPTY = 3 * kMaxBuf + 2 };
+    auto BAR = [&](int which, int idx) { return bar0 + 8u * static_cast<uint32_t>(which + idx); };
+    const int tile_cols = TN + q.pmax;
+    const uint32_t raw_bytes = static_cast<uint32_t>(tile_cols) * TB * 4u;        // one fp32 tile incl. halo columns
+    const bool f16 = (q.fmt == FMT_F16_SCALED);
     // a tile whose N + P columns are plain, aligned memory can be fetched by one bulk copy
-    auto tile_lo = [&](long long ipA) { return (p.dir > 0) ? ipA : (p.n_v - ipA - static_cast<long long>(TN + q.pmax) * TB); };
+    auto tile_lo = [&](long long ipA) { return (p.dir > 0) ? ipA : (p.n_v - ipA - static_cast<long long>(tile_cols) * TB); };
     auto tile_bulk = [&](long long ipA) {
         const long long lo = tile_lo(ipA);
-        return q.fast_ok && lo >= q.fast_lo && lo + static_cast<long long>(TN + q.pmax) * TB <= q.fast_hi;
+        return q.fast_ok && lo >= q.fast_lo && lo + static_cast<long long>(tile_cols) * TB <= q.fast_hi;
     };
+    auto tile_ipA = [&](int ct) { return (q.first_col + static_cast<long long>(ct) * TN - q.pmax) * TB - q.org; };
 
     // ---- one-time set-up: barriers, TMEM, the 8x-expanded (Hankel) tap arrays ------------------------------
     if (tid == 0) {
+        for (int i = 0; i < kMaxBuf; ++i) {
+            mbar_init(BAR(RAW_FULL, i), 1);
+            mbar_init(BAR(SLAB_FULL, i), kLoadThreads);
+            mbar_init(BAR(BUF_EMPTY, i), 1);
+        }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(BAR(SLAB_FULL, i), kLoadWarps * 32);
-            mbar_init(BAR(SLAB_EMPTY, i), 1);
             mbar_init(BAR(ACC_FULL, i), 1);
             mbar_init(BAR(ACC_EMPTY, i), kEpiWarps * 32);
-            mbar_init(BAR(RAW_FULL, i), 1);
-            mbar_init(BAR(RAW_EMPTY, i), kLoadWarps * 32);
         }
         fence_mbar_init();
     }
@@ -216,17 +319,30 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     {
         // H[u][i][e] = g[8u + i + e],  g[w] = c[128 P + 127 - w]  (zero outside [0, k))
         const int top = TB * q.pmax + (TB - 1);
+        uint16_t* H = reinterpret_cast<uint16_t*>(smem_raw);
+        const uint32_t hank_elems = hank_bytes >> 1;
         for (int idx = tid; idx < q.hank_cores * 64; idx += kToepThreads) {
             const int u = idx >> 6, i = (idx >> 3) & 7, e = idx & 7;
             const int ci = top - (8 * u + i + e);
             const float c = (ci >= 0 && ci < q.k) ? taps.c[ci] : 0.f;
-            const __nv_bfloat16 h = __float2bfloat16_rn(c);
-            const float r1 = c - __bfloat162float(h);
-            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-            __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-            H[idx] = h;
-            H[(hank_bytes >> 1) + idx] = m;
-            if (q.nver > 2) H[2 * (hank_bytes >> 1) + idx] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+            uint16_t h16, m16, l16;
+            if (f16) {
+                const float cs = c * q.tap_scale;
+                const __half h = __float2half_rn(cs);
+                const float r1 = cs - __half2float(h);
+                const __half m = __float2half_rn(r1);
+                const __half l = __float2half_rn(r1 - __half2float(m));
+                h16 = __half_as_ushort(h); m16 = __half_as_ushort(m); l16 = __half_as_ushort(l);
+            } else {
+                const __nv_bfloat16 h = __float2bfloat16_rn(c);
+                const float r1 = c - __bfloat162float(h);
+                const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+                const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+                h16 = __bfloat16_as_ushort(h); m16 = __bfloat16_as_ushort(m); l16 = __bfloat16_as_ushort(l);
+            }
+            H[idx] = h16;
+            H[hank_elems + idx] = m16;
+            if (q.nver > 2) H[2 * hank_elems + idx] = l16;
         }
     }
     fence_proxy_async_smem();                              // H is read by the tensor core (async proxy)
@@ -236,75 +352,38 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     const uint32_t tmem_base = tmem_base_holder;
 
     const int ntiles = q.total_tiles;
+    const int nbuf = q.nbuf;
     if (warp == kTmaWarp) {
-        // ===== TMA PRODUCER (short filters): whole fp32 tiles, two ahead, by cp.async.bulk ==================
-        if (q.raw_stages && lane == 0) {
-            int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int rs = it & 1;
-                mbar_wait(BAR(RAW_EMPTY, rs), ((it >> 1) & 1) ^ 1u);
+        // ===== TMA PRODUCER (in-place mode): whole fp32 tiles by cp.async.bulk, as soon as a buffer is free ===
+        if (q.mode == MODE_INPLACE && lane == 0) {
+            int buf = 0;
+            uint32_t par = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                mbar_wait(BAR(BUF_EMPTY, buf), par ^ 1u);
                 const int row = t / q.tiles_per_row;
                 const int ct = t - row * q.tiles_per_row;
-                const long long ipA = (q.first_col + static_cast<long long>(ct) * TN - q.pmax) * TB - q.org;
+                const long long ipA = tile_ipA(ct);
                 if (tile_bulk(ipA)) {
-                    mbar_arrive_expect_tx(BAR(RAW_FULL, rs), raw_bytes);
-                    bulk_copy_g2s(smem0 + raw0_off + static_cast<uint32_t>(rs) * raw_bytes,
-                                  p.x + static_cast<long long>(row) * p.ld_x + tile_lo(ipA) + p.in_off, raw_bytes, BAR(RAW_FULL, rs));
+                    mbar_arrive_expect_tx(BAR(RAW_FULL, buf), raw_bytes);
+                    bulk_copy_g2s(smem0 + buf0_off + static_cast<uint32_t>(buf) * q.buf_bytes,
+                                  p.x + static_cast<long long>(row) * p.ld_x + tile_lo(ipA) + p.in_off, raw_bytes, BAR(RAW_FULL, buf));
                 } else {
-                    mbar_arrive(BAR(RAW_FULL, rs));        // edge tile: the converters synthesise it
+                    mbar_arrive(BAR(RAW_FULL, buf));       // edge tile: the converters synthesise it from global memory
                 }
+                if (++buf == nbuf) { buf = 0; par ^= 1u; }
             }
-        }
-    } else if (warp >= kEpiWarps && warp < kEpiWarps + kLoadWarps && q.raw_stages) {
-        // ===== CONVERTER (short filters): raw fp32 tile in smem -> split-BF16 core-matrix rows ===============
-        const int tl = tid - kEpiWarps * 32;
-        const int len = (TN + q.pmax) * TB;
-        const int nitems = (TN + q.pmax) * 16;
-        int it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int rs = it & 1;
-            const int stage = (q.stages == 2) ? (it & 1) : 0;
-            const uint32_t par = ((q.stages == 2) ? (it >> 1) : it) & 1;
-            const int row = t / q.tiles_per_row;
-            const int ct = t - row * q.tiles_per_row;
-            const long long ipA = (q.first_col + static_cast<long long>(ct) * TN - q.pmax) * TB - q.org;
-            const bool bulk = tile_bulk(ipA);
-            float* raw = reinterpret_cast<float*>(smem_raw + raw0_off + static_cast<uint32_t>(rs) * raw_bytes);
-            mbar_wait(BAR(RAW_FULL, rs), (it >> 1) & 1);
-            if (!bulk) {                                   // zero / held / extended samples, causal order
-                const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
-                for (int i = tl; i < len; i += kLoadWarps * 32)
-                    raw[i] = tload(p, xr, (p.dir > 0) ? (ipA + i) : (p.n_v - 1 - (ipA + i)));
-                asm volatile("bar.sync 1, %0;" ::"n"(kLoadWarps * 32) : "memory");
-            }
-            mbar_wait(BAR(SLAB_EMPTY, stage), par ^ 1u);
-            const uint32_t sbase = slab0 + static_cast<uint32_t>(stage) * stage_bytes;
-            const bool rev = bulk && p.dir < 0;            // bulk tiles of an anticausal pass sit in ascending memory order
-            for (int item = tl; item < nitems; item += kLoadWarps * 32) {
-                const int cidx = item >> 4, sc = item & 15;
-                const int o = cidx * TB + sc * 8;
-                const float* src = rev ? (raw + (len - 8 - o)) : (raw + o);
-                const float4 a = *reinterpret_cast<const float4*>(src);
-                const float4 b = *reinterpret_cast<const float4*>(src + 4);
-                float v[8];
-                v[0] = rev ? b.w : a.x; v[1] = rev ? b.z : a.y; v[2] = rev ? b.y : a.z; v[3] = rev ? b.x : a.w;
-                v[4] = rev ? a.w : b.x; v[5] = rev ? a.z : b.y; v[6] = rev ? a.y : b.z; v[7] = rev ? a.x : b.w;
-                split_store(v, q.nver, sbase + (static_cast<uint32_t>(sc) * q.slab_cols + cidx) * 16u, ver_bytes);
-            }
-            fence_proxy_async_smem();                      // my generic-proxy writes -> visible to the MMA's async reads
-            mbar_arrive(BAR(SLAB_FULL, stage));
-            mbar_arrive(BAR(RAW_EMPTY, rs));               // raw[rs] may be overwritten by the next bulk copy
         }
     } else if (warp >= kEpiWarps && warp < kEpiWarps + kLoadWarps) {
-        // ===== LOADER (long filters): stage the tile's N + P columns as split-BF16 core-matrix rows ==========
-        // A thread owns items tl, tl + 256, ... (item = (column, 8-sample chunk)); its share of the NEXT
-        // tile is fetched into registers right after the current one is stored, so the HBM latency is
-        // spent while the tensor core works and only the convert + STS.128 phase waits on slab_empty.
-        constexpr int RMAX = ((TN + 32) * 16 + kLoadWarps * 32 - 1) / (kLoadWarps * 32);      // pmax <= 32 on this path
+        // ===== LOADER / CONVERTER: stage the tile's N + P columns as split 16-bit core-matrix rows ============
+        // A thread owns items tl, tl + 256, ... (item = (column, 8-sample chunk)).
         const int tl = tid - kEpiWarps * 32;
-        const int nitems = (TN + q.pmax) * 16;
+        const int lw = tl >> 5;
+        const int nitems = tile_cols * 16;
+        const bool inplace = (q.mode == MODE_INPLACE);
         float4 raw[RMAX][2];
-        uint32_t fastmask = 0;
+        uint32_t fastmask = 0;                             // items loaded in ascending memory order (anticausal: to be reversed)
+        uint32_t mx = 0;
+        // gather from global memory: fast aligned chunks by LDG.128, edge chunks rule by rule
         auto fetch = [&](int t) {
             const int row = t / q.tiles_per_row;
             const int ct = t - row * q.tiles_per_row;
@@ -313,7 +392,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             fastmask = 0;
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
-                const int item = tl + r * (kLoadWarps * 32);
+                const int item = tl + r * kLoadThreads;
                 if (item < nitems) {
                     const int cidx = item >> 4, sc = item & 15;
                     const long long ip0 = (j0 - q.pmax + cidx) * TB + sc * 8 - q.org;   // causal index of the chunk's first sample
@@ -333,71 +412,122 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
                 }
             }
         };
-        int it = 0;
-        if (static_cast<int>(blockIdx.x) < ntiles) fetch(blockIdx.x);
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int stage = (q.stages == 2) ? (it & 1) : 0;
-            const uint32_t par = ((q.stages == 2) ? (it >> 1) : it) & 1;
-            mbar_wait(BAR(SLAB_EMPTY, stage), par ^ 1u);
-            const uint32_t sbase = slab0 + static_cast<uint32_t>(stage) * stage_bytes;
+        // gather from a raw fp32 tile in shared memory (ascending memory order)
+        auto gather_smem = [&](const float* rawt) {
+            const int len = tile_cols * TB;
+            const bool rev = p.dir < 0;
+            fastmask = rev ? 0xffffffffu : 0u;
 #pragma unroll
             for (int r = 0; r < RMAX; ++r) {
-                const int item = tl + r * (kLoadWarps * 32);
+                const int item = tl + r * kLoadThreads;
                 if (item < nitems) {
-                    const int cidx = item >> 4, sc = item & 15;
-                    const float4 a = raw[r][0], b = raw[r][1];
-                    const bool rev = (p.dir < 0) && ((fastmask >> r) & 1u);   // fast anticausal chunks were loaded ascending
-                    float v[8];
-                    v[0] = rev ? b.w : a.x; v[1] = rev ? b.z : a.y; v[2] = rev ? b.y : a.z; v[3] = rev ? b.x : a.w;
-                    v[4] = rev ? a.w : b.x; v[5] = rev ? a.z : b.y; v[6] = rev ? a.y : b.z; v[7] = rev ? a.x : b.w;
-                    split_store(v, q.nver, sbase + (static_cast<uint32_t>(sc) * q.slab_cols + cidx) * 16u, ver_bytes);
+                    const int o = item * 8;                                    // causal offset of the chunk in the tile
+                    const float* src = rev ? (rawt + (len - 8 - o)) : (rawt + o);
+                    raw[r][0] = *reinterpret_cast<const float4*>(src);
+                    raw[r][1] = *reinterpret_cast<const float4*>(src + 4);
                 }
             }
-            fence_proxy_async_smem();                      // my generic-proxy writes -> visible to the MMA's async reads
-            mbar_arrive(BAR(SLAB_FULL, stage));
-            if (t + static_cast<int>(gridDim.x) < ntiles) fetch(t + gridDim.x);
+        };
+        auto local_max = [&]() {
+            mx = 0;
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r)
+                if (tl + r * kLoadThreads < nitems) mx = max(mx, absmax_bits(raw[r][0], raw[r][1]));
+        };
+        // block-wide max -> power-of-two scale (fmt 0); the named barrier doubles as the "everyone has
+        // read the raw tile" point of the in-place conversion
+        auto slab_scale = [&](int it) -> float {
+            if (!f16) {
+                if (inplace) asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
+                return 1.f;
+            }
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0) red_slots[it & 1][lw] = wm;
+            asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < kLoadWarps; ++w) m = max(m, *(volatile uint32_t*)&red_slots[it & 1][w]);
+            // scale = 2^(141 - E): max|x| * scale in [2^14, 2^15); exponent field kept in [14, 253] so that
+            // both the scale and its inverse are normal numbers
+            const int e = static_cast<int>(m >> 23);
+            const int sexp = min(268 - e, 253);
+            const float scale = __uint_as_float(static_cast<uint32_t>(sexp) << 23);
+            if (tl == 0) inv_scale_ring[it & 7] = __uint_as_float(static_cast<uint32_t>(254 - sexp) << 23);
+            return scale;
+        };
+        auto store_slab = [&](uint32_t sbase, float scale) {
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int item = tl + r * kLoadThreads;
+                if (item < nitems) {
+                    const int cidx = item >> 4, sc = item & 15;
+                    const bool rev = (p.dir < 0) && ((fastmask >> r) & 1u);
+                    const uint32_t dst = sbase + (static_cast<uint32_t>(sc) * q.slab_cols + cidx) * 16u;
+                    if (f16) split_store<true>(raw[r][0], raw[r][1], rev, scale, q.nver, dst, ver_bytes);
+                    else split_store<false>(raw[r][0], raw[r][1], rev, 1.f, q.nver, dst, ver_bytes);
+                }
+            }
+        };
+
+        int it = 0, buf = 0;
+        uint32_t par = 0;
+        if (inplace) {
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int row = t / q.tiles_per_row;
+                const int ct = t - row * q.tiles_per_row;
+                const uint32_t boff = buf0_off + static_cast<uint32_t>(buf) * q.buf_bytes;
+                mbar_wait(BAR(RAW_FULL, buf), par);        // bulk copy landed (or: buffer is free, edge tile)
+                if (tile_bulk(tile_ipA(ct))) gather_smem(reinterpret_cast<const float*>(smem_raw + boff));
+                else fetch(t);
+                local_max();
+                const float scale = slab_scale(it);        // barrier: every converter holds its part of the tile
+                store_slab(smem0 + boff, scale);
+                fence_proxy_async_smem();                  // my generic-proxy writes -> visible to the MMA's async reads
+                mbar_arrive(BAR(SLAB_FULL, buf));
+                if (++buf == nbuf) { buf = 0; par ^= 1u; }
+            }
+        } else {
+            // the thread's share of the NEXT tile is fetched into registers right after the current one is
+            // stored, so the HBM latency is spent while the tensor core works and only the convert +
+            // STS.128 phase waits on buf_empty
+            if (static_cast<int>(blockIdx.x) < ntiles) fetch(blockIdx.x);
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                local_max();
+                const float scale = slab_scale(it);
+                mbar_wait(BAR(BUF_EMPTY, buf), par ^ 1u);
+                store_slab(smem0 + buf0_off + static_cast<uint32_t>(buf) * q.buf_bytes, scale);
+                fence_proxy_async_smem();
+                mbar_arrive(BAR(SLAB_FULL, buf));
+                if (t + static_cast<int>(gridDim.x) < ntiles) fetch(t + gridDim.x);
+                if (++buf == nbuf) { buf = 0; par ^= 1u; }
+            }
         }
     } else if (warp == kMmaWarp) {
         // ===== MMA ISSUER ===================================================================================
-        int it = 0;
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc(q.fmt);
+        const uint32_t a_lo0 = desc_lo(smem0, 128u);
+        const uint32_t hank16 = hank_bytes >> 4, ver16 = ver_bytes >> 4;
+        const uint32_t lbo_x = static_cast<uint32_t>(q.slab_cols) * 16u;
+        int it = 0, buf = 0;
+        uint32_t par = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int stage = (q.stages == 2) ? (it & 1) : 0;
-            const uint32_t spar = ((q.stages == 2) ? (it >> 1) : it) & 1;
             const int acc = it & 1;
             const uint32_t apar = (it >> 1) & 1;
             mbar_wait(BAR(ACC_EMPTY, acc), apar ^ 1u);
-            mbar_wait(BAR(SLAB_FULL, stage), spar);
+            mbar_wait(BAR(SLAB_FULL, buf), par);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sbase = slab0 + static_cast<uint32_t>(stage) * stage_bytes;
-                const uint32_t lbo_b = static_cast<uint32_t>(q.slab_cols) * 16u;
-                const uint32_t dcol = tmem_base + static_cast<uint32_t>(acc * TN);
-                // only the 14-bit start-address field changes between MMAs: add offsets in 16-byte units
-                const uint64_t a_h0 = smem_desc(smem0, 128u, 128u), x_h0 = smem_desc(sbase, lbo_b, 128u);
-                const uint64_t hank16 = hank_bytes >> 4, ver16 = ver_bytes >> 4;
-                const int terms = q.terms;
-                uint32_t accum = 0;
-                for (int pb = 0; pb <= q.pmax; ++pb) {
-                    const int s_lo = max(0, TB * pb - (q.k - 1));       // first s with a non-zero tap in T_p
-                    for (int ks = s_lo >> 4; ks < TB / 16; ++ks) {
-                        const uint64_t a_h = a_h0 + static_cast<uint64_t>(8 * (16 * (q.pmax - pb) + 2 * ks));
-                        const uint64_t x_h = x_h0 + static_cast<uint64_t>(2 * ks * q.slab_cols + (q.pmax - pb));
-                        const uint64_t a_m = a_h + hank16, x_m = x_h + ver16;
-                        tc_mma_bf16(dcol, a_h, x_h, kIdesc, accum);     // hi * hi
-                        tc_mma_bf16(dcol, a_h, x_m, kIdesc, 1u);        // hi * mid
-                        tc_mma_bf16(dcol, a_m, x_h, kIdesc, 1u);        // mid * hi
-                        if (terms >= 4) tc_mma_bf16(dcol, a_m, x_m, kIdesc, 1u);
-                        if (terms == 6) {
-                            tc_mma_bf16(dcol, a_h, x_m + ver16, kIdesc, 1u);     // hi * lo
-                            tc_mma_bf16(dcol, a_m + hank16, x_h, kIdesc, 1u);    // lo * hi
-                        }
-                        accum = 1;
-                    }
-                }
-                tc_commit(BAR(SLAB_EMPTY, stage));         // slab may be refilled once these MMAs retire
+            const uint32_t x_lo0 = desc_lo(smem0 + buf0_off + static_cast<uint32_t>(buf) * q.buf_bytes, lbo_x);
+            const uint32_t dcol = tmem_base + static_cast<uint32_t>(acc * TN);
+            if (q.terms == 3) issue_tile<3>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc);
+            else if (q.terms == 4) issue_tile<4>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc);
+            else issue_tile<6>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc);
+            if (leader) {
+                tc_commit(BAR(BUF_EMPTY, buf));            // buffer may be refilled once these MMAs retire
                 tc_commit(BAR(ACC_FULL, acc));             // accumulator complete
             }
             __syncwarp();
+            if (++buf == nbuf) { buf = 0; par ^= 1u; }
         }
     } else {
         // ===== EPILOGUE: TMEM -> registers -> coalesced row stores ==========================================
@@ -412,6 +542,9 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
             mbar_wait(BAR(ACC_FULL, acc), apar);
             tc_fence_after();
+            // un-scale: exact powers of two (1 in BF16 mode); written by the loaders long before ACC_FULL
+            const float inv_x = f16 ? *(volatile float*)&inv_scale_ring[it & 7] : 1.f;
+            const float inv_c = q.tap_inv;
             const long long ip_first = j0 * TB - q.org, ip_last = (j0 + TN) * TB - q.org;      // this tile's outputs [first, last)
             const bool interior = ip_first >= q.ip_lo && ip_last <= q.ip_hi;
 #pragma unroll 1
@@ -423,16 +556,16 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
                     float* yb = yr + map_index(p, ipb);
                     if (p.dir > 0) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) yb[c * TB] = __uint_as_float(v[c]);
+                        for (int c = 0; c < 32; ++c) yb[c * TB] = __uint_as_float(v[c]) * inv_x * inv_c;
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) yb[-c * TB] = __uint_as_float(v[c]);
+                        for (int c = 0; c < 32; ++c) yb[-c * TB] = __uint_as_float(v[c]) * inv_x * inv_c;
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const long long ip = ipb + static_cast<long long>(c) * TB;
-                        if (ip >= q.ip_lo && ip < q.ip_hi) yr[map_index(p, ip)] = __uint_as_float(v[c]);
+                        if (ip >= q.ip_lo && ip < q.ip_hi) yr[map_index(p, ip)] = __uint_as_float(v[c]) * inv_x * inv_c;
                     }
                 }
             }
@@ -454,31 +587,49 @@ struct ToepPlan {
     size_t smem_bytes;
 };
 
-bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, ToepPlan* out)
+bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k, ToepPlan* out)
 {
     if (k < 1 || k > SCIR_B200_MAX_TAPS) return false;
     ToepParams q{};
     q.p = pass;
     q.k = static_cast<int>(k);
     q.pmax = static_cast<int>((k - 1 + (TB - 1)) / TB);
-    if (q.pmax > 32) return false;                         // loader register budget (RMAX) and shared memory
+    if (q.pmax > kPmaxLimit) return false;                 // loader register budget (RMAX) and shared memory
     q.hank_cores = 16 * q.pmax + 31;
     q.slab_cols = (TN + q.pmax) | 1;
+    q.fmt = (ctx->opt.toeplitz_split == 1) ? FMT_BF16 : FMT_F16_SCALED;
     int64_t terms = ctx->opt.toeplitz_terms;
-    if (terms != 3 && terms != 4 && terms != 6) terms = 4;
+    if (terms != 3 && terms != 4 && terms != 6) terms = 3;
     q.terms = static_cast<int>(terms);
     q.nver = (terms == 6) ? 3 : 2;
     const size_t hank = static_cast<size_t>(q.hank_cores) * 128 * q.nver;
-    const size_t stage = static_cast<size_t>(16) * q.slab_cols * 16 * q.nver;
-    const size_t budget = static_cast<size_t>(ctx->max_smem_optin) - 1024;        // static smem + slack
-    if (hank + stage > budget) return false;
+    const size_t slab = static_cast<size_t>(16) * q.slab_cols * 16 * q.nver;
     const size_t raw = static_cast<size_t>(TN + q.pmax) * TB * 4;
-    if (ctx->opt.toeplitz_loader != 1 && hank + stage + 2 * raw <= budget) {
-        q.raw_stages = 2;                                  // short filters: TMA-prefetched fp32 ring + converter warps
-        q.stages = (hank + 2 * stage + 2 * raw <= budget) ? 2 : 1;
+    const size_t budget = static_cast<size_t>(ctx->max_smem_optin) - 1024;        // static smem + slack
+    auto up128 = [](size_t v) { return (v + 127) / 128 * 128; };
+    if (ctx->opt.toeplitz_loader != 1 && hank + 3 * up128(std::max(slab, raw)) <= budget) {
+        q.mode = MODE_INPLACE;                             // short filters: TMA-fed buffers converted in place
+        q.nbuf = 3;
+        q.buf_bytes = static_cast<unsigned>(up128(std::max(slab, raw)));
     } else {
-        q.raw_stages = 0;                                  // long filters: register prefetch (no smem left for a ring)
-        q.stages = (hank + 2 * stage <= budget) ? 2 : 1;
+        q.mode = MODE_REGISTER;                            // long filters: register prefetch
+        q.buf_bytes = static_cast<unsigned>(up128(slab));
+        if (hank + q.buf_bytes > budget) return false;
+        q.nbuf = (hank + 2 * static_cast<size_t>(q.buf_bytes) <= budget) ? 2 : 1;
+    }
+    // FP16 block scaling of the taps: max|c| * tap_scale in [2^14, 2^15)
+    q.tap_scale = 1.f;
+    q.tap_inv = 1.f;
+    if (q.fmt == FMT_F16_SCALED && c != nullptr) {
+        float cmax = 0.f;
+        for (int64_t i = 0; i < k; ++i) cmax = std::max(cmax, std::fabs(c[i]));
+        if (cmax > 0.f && std::isfinite(cmax)) {
+            int e = 0;
+            std::frexp(cmax, &e);                          // cmax = m * 2^e, m in [0.5, 1)
+            const int se = std::min(std::max(15 - e, -120), 120);
+            q.tap_scale = std::ldexp(1.f, se);
+            q.tap_inv = std::ldexp(1.f, -se);
+        }
     }
     // outputs wanted, in causal index space i'
     q.ip_lo = (pass.dir > 0) ? pass.out_begin : (pass.n_v - pass.out_end);
@@ -503,7 +654,7 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, ToepPla
     }
     q.fast_ok = aligned16(pass.x) && (pass.ld_x % 4 == 0);
     out->q = q;
-    out->smem_bytes = hank + static_cast<size_t>(q.stages) * stage + static_cast<size_t>(q.raw_stages) * raw;
+    out->smem_bytes = hank + static_cast<size_t>(q.nbuf) * q.buf_bytes;
     return true;
 }
 
@@ -512,14 +663,14 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, ToepPla
 bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k)
 {
     ToepPlan plan;
-    return pass.batch > 0 && pass.out_end > pass.out_begin && make_plan(ctx, pass, k, &plan);
+    return pass.batch > 0 && pass.out_end > pass.out_begin && make_plan(ctx, pass, nullptr, k, &plan);
 }
 
 int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
 {
     if (pass.batch <= 0 || pass.out_end <= pass.out_begin) return SCIR_B200_OK;
     ToepPlan plan;
-    if (!make_plan(ctx, pass, k, &plan))
+    if (!make_plan(ctx, pass, c, k, &plan))
         return set_error(SCIR_B200_ERR_UNSUPPORTED, "tcgen05 Toeplitz path cannot serve k=%lld", (long long)k);
     SCIR_TRY(ctx_bind(ctx));
     thread_local ToepTaps* tl = nullptr;

@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace scir_b200 {
 
 namespace {
@@ -45,6 +47,63 @@ struct PolyParams {
     int nchunk;
     int in_vec_ok, out_vec_ok;
 };
+
+// The FFMA core shared by the tile and the streaming kernel: R = UP*G outputs of one thread, x-major over the
+// window, taps as constant-bank operands.  wbase points at the thread's sample q0_thread.
+template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
+__device__ __forceinline__ void poly_core(float (&acc)[UP * G], const float* wbase, int nchunk, const PolyTaps& taps)
+{
+    constexpr int R = UP * G;
+    constexpr int ZP = (Z > 0) ? 4 : 0;
+    constexpr int DQMAX = ((R - 1) * DOWN) / UP;
+    constexpr int W4 = (KCP + ZP + DQMAX + 1 + 3) / 4;
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0.f;
+    auto chunk = [&](int c) {
+        // window: samples q0_thread - (c+1)*KCP - ZP + s, s in [0, 4*W4)
+        const float4* w = reinterpret_cast<const float4*>(wbase - (c + 1) * KCP - ZP);
+        const float* tc = taps.c + c * (KCP * UP);
+#pragma unroll
+        for (int v4 = 0; v4 < W4; ++v4) {
+            const float4 v = w[v4];
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = 4 * v4 + e;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int tj = (j * DOWN) % UP;
+                    const int dq = (j * DOWN) / UP;
+                    const int ot = (tj < Z) ? 1 : 0;
+                    const int il = dq + KCP + ZP - s - ot;          // chunk-local tap index of this sample
+                    if (il >= 0 && il < KCP) acc[j] = fmaf(tc[(il + ot) * UP + tj], xv[e], acc[j]);
+                }
+            }
+        }
+    };
+    if constexpr (NCH > 0) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) chunk(c);
+    } else {
+        for (int c = 0; c < nchunk; ++c) chunk(c);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void poly_store_acc(float* so, const float (&acc)[R])
+{
+    if constexpr (R % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 4)
+            *reinterpret_cast<float4*>(so + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    } else if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 2) *reinterpret_cast<float2*>(so + j) = make_float2(acc[j], acc[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) so[j] = acc[j];
+    }
+}
 
 // UP/DOWN: rate; G: groups of `up` outputs per thread; KCP: taps per phase per chunk; Z: leading
 // zero taps; NCH: compile-time chunk count (0 = runtime loop, taps through LDCU).
@@ -99,52 +158,10 @@ upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant_
     }
 
     float acc[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = 0.f;
-
-    const float* wbase = smem + HALO + tid * SIN;          // sample q0_thread
-    auto chunk = [&](int c) {
-        // window: samples q0_thread - (c+1)*KCP - ZP + s, s in [0, 4*W4)
-        const float4* w = reinterpret_cast<const float4*>(wbase - (c + 1) * KCP - ZP);
-        const float* tc = taps.c + c * (KCP * UP);
-#pragma unroll
-        for (int v4 = 0; v4 < W4; ++v4) {
-            const float4 v = w[v4];
-            const float xv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int s = 4 * v4 + e;
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int tj = (j * DOWN) % UP;
-                    const int dq = (j * DOWN) / UP;
-                    const int ot = (tj < Z) ? 1 : 0;
-                    const int il = dq + KCP + ZP - s - ot;          // chunk-local tap index of this sample
-                    if (il >= 0 && il < KCP) acc[j] = fmaf(tc[(il + ot) * UP + tj], xv[e], acc[j]);
-                }
-            }
-        }
-    };
-    if constexpr (NCH > 0) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) chunk(c);
-    } else {
-        for (int c = 0; c < nchunk; ++c) chunk(c);
-    }
+    poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, smem + HALO + tid * SIN, nchunk, taps);
 
     __syncthreads();                                        // every warp is done reading the tile
-    float* so = smem + tid * R;
-    if constexpr (R % 4 == 0) {
-#pragma unroll
-        for (int j = 0; j < R; j += 4)
-            *reinterpret_cast<float4*>(so + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-    } else if constexpr (R % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < R; j += 2) *reinterpret_cast<float2*>(so + j) = make_float2(acc[j], acc[j + 1]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j) so[j] = acc[j];
-    }
+    poly_store_acc<R>(smem + tid * R, acc);
 
     const bool bulk_out = q.out_vec_ok && m0 >= q.m_begin && m0 + TILE_OUT <= q.m_end;
     if (bulk_out) {
@@ -163,21 +180,162 @@ upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant_
     }
 }
 
+// ---- the streaming kernel (default): persistent CTAs, double-buffered TMA bulk loads --------------------
+// Same tiles as upfirdn_tile_kernel, but a CTA walks tiles w = blockIdx.x, +gridDim.x, ...: two input
+// stages are filled by cp.async.bulk two tiles ahead (one elected thread, `full` mbarriers), results leave
+// through a third buffer whose bulk store drains while the next tile is being computed.  Index set-up,
+// barrier init and the first DRAM round trip are paid once per CTA instead of once per tile, and a CTA
+// never sits idle on its own load: at the ridge (config 4 is HBM- and FP32-bound at once) that overlap is
+// the whole game.
 template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
-int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid)
+__global__ void __launch_bounds__(kPolyNT, 3)
+upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps, long long batch)
+{
+    constexpr int NT = kPolyNT;
+    constexpr int R = UP * G;
+    constexpr int SIN = DOWN * G;
+    static_assert(SIN % 4 == 0 && (SIN / 4) % 2 == 1, "dense tile must be conflict-free for LDS.128");
+    static_assert(KCP % 4 == 0 && Z < UP, "chunk geometry");
+    constexpr int TILE_OUT = NT * R;
+    constexpr int TILE_IN = NT * SIN;
+    constexpr int ZP = (Z > 0) ? 4 : 0;
+
+    extern __shared__ __align__(128) float smem[];     // in[0] | in[1] | out
+    __shared__ __align__(8) unsigned long long full[2];
+
+    const int tid = threadIdx.x;
+    const int nchunk = (NCH > 0) ? NCH : q.nchunk;
+    const int HALO = nchunk * KCP + ZP;
+    const int len = HALO + TILE_IN + 4;
+    float* const out_s = smem + 2 * len;
+    const uint32_t bar0 = smem_u32(&full[0]);
+    const long long GD = gridDim.x;
+    const long long step_row = GD / q.ntiles, step_tile = GD - step_row * q.ntiles;
+
+    long long row = blockIdx.x / q.ntiles, tile = blockIdx.x - row * q.ntiles;
+    long long nrow = row, ntile = tile;                    // runs two tiles ahead
+    auto advance = [&](long long& r, long long& t) {
+        r += step_row;
+        t += step_tile;
+        if (t >= q.ntiles) {
+            t -= q.ntiles;
+            r += 1;
+        }
+    };
+    auto first_sample = [&](long long t) {
+        const long long m0 = q.base_m + t * TILE_OUT;
+        return (m0 / UP) * DOWN - HALO;
+    };
+    auto can_bulk = [&](long long a) { return q.in_vec_ok && a >= 0 && a + len <= q.n_in; };
+    auto prefetch = [&](long long r, long long t, int s) { // thread 0 only
+        if (r >= batch) return;
+        const long long a = first_sample(t);
+        if (!can_bulk(a)) return;
+        mbar_arrive_expect_tx(bar0 + 8u * s, static_cast<uint32_t>(len) * 4u);
+        bulk_copy_g2s(smem_u32(smem + s * len), q.x + r * q.ld_x + a, static_cast<uint32_t>(len) * 4u, bar0 + 8u * s);
+    };
+
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_mbar_init();
+        prefetch(nrow, ntile, 0);
+    }
+    advance(nrow, ntile);
+    if (tid == 0) prefetch(nrow, ntile, 1);
+    advance(nrow, ntile);
+    __syncthreads();                                       // barrier init visible to the waiters
+
+    uint32_t phases = 0;                                   // bit s = parity to wait for on full[s]
+    for (int it = 0; row < batch; ++it) {
+        const int s = it & 1;
+        const long long m0 = q.base_m + tile * TILE_OUT;
+        const long long a = first_sample(tile);
+        const float* __restrict__ xr = q.x + row * q.ld_x;
+        float* __restrict__ yr = q.y + row * q.ld_y;
+        float* const in = smem + s * len;
+
+        if (can_bulk(a)) {
+            mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
+            phases ^= 1u << s;
+        } else {                                           // edge tile: mode='constant', cval 0
+            for (int t = tid; t < len; t += NT) {
+                const long long xi = a + t;
+                in[t] = (xi >= 0 && xi < q.n_in) ? xr[xi] : 0.f;
+            }
+            __syncthreads();
+        }
+
+        float acc[R];
+        poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, in + HALO + tid * SIN, nchunk, taps);
+
+        if (tid == 0) bulk_store_wait_read<0>();           // the previous tile's store has drained `out`
+        __syncthreads();                                   // A: in[s] consumed by every warp, out free
+        if (tid == 0) prefetch(nrow, ntile, s);            // refill in[s] two tiles ahead
+
+        poly_store_acc<R>(out_s + tid * R, acc);
+
+        const bool bulk_out = q.out_vec_ok && m0 >= q.m_begin && m0 + TILE_OUT <= q.m_end;
+        if (bulk_out) {
+            fence_proxy_async_smem();                      // generic-proxy writes -> async proxy
+            __syncthreads();                               // B
+            if (tid == 0) bulk_copy_s2g(yr + (m0 - q.m_begin), smem_u32(out_s), TILE_OUT * 4u);
+        } else {
+            __syncthreads();
+            for (int t = tid; t < TILE_OUT; t += NT) {
+                const long long m = m0 + t;
+                if (m >= q.m_begin && m < q.m_end) yr[m - q.m_begin] = out_s[t];
+            }
+        }
+        advance(row, tile);
+        advance(nrow, ntile);
+    }
+    if (tid == 0) bulk_store_wait_read<0>();               // smem must outlive the last store's read
+}
+
+template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
+int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid, long long batch)
 {
     constexpr int R = UP * G, SIN = DOWN * G;
     const int halo = nchunk * KCP + ((Z > 0) ? 4 : 0);
-    const size_t floats = std::max<size_t>(static_cast<size_t>(halo) + kPolyNT * SIN + 4, static_cast<size_t>(kPolyNT) * R);
+    const size_t len = static_cast<size_t>(halo) + kPolyNT * SIN + 4;
+    const size_t stream_bytes = (2 * len + static_cast<size_t>(kPolyNT) * R) * sizeof(float);
+    const int d = ctx->device & 15;
+    if (ctx->opt.upfirdn_variant != 3 && stream_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
+        // persistent grid: every SM holds as many CTAs as fit; each walks tiles with stride gridDim.x
+        auto kern = upfirdn_stream_kernel<UP, DOWN, G, KCP, Z, NCH>;
+        static thread_local size_t configured[16] = {0};
+        static thread_local size_t occ_smem[16] = {0};
+        static thread_local int resident[16] = {0};
+        if (configured[d] < stream_bytes) {
+            SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stream_bytes)),
+                      "cudaFuncSetAttribute(upfirdn_stream_kernel)");
+            configured[d] = stream_bytes;
+        }
+        if (resident[d] == 0 || occ_smem[d] != stream_bytes) {
+            int nb = 0;
+            SCIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPolyNT, stream_bytes),
+                      "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            resident[d] = std::max(nb, 1);
+            occ_smem[d] = stream_bytes;
+        }
+        const long long g = std::min<long long>(grid, static_cast<long long>(ctx->sm_count) * resident[d]);
+        kern<<<static_cast<unsigned>(g), kPolyNT, stream_bytes, ctx->stream>>>(q, taps, batch);
+        SCIR_CUDA(cudaGetLastError(), "upfirdn_stream_kernel launch");
+        ctx->launches++;
+        ctx->poly_launches++;
+        return SCIR_B200_OK;
+    }
+    const size_t floats = std::max<size_t>(len, static_cast<size_t>(kPolyNT) * R);
     const size_t smem_bytes = floats * sizeof(float);
     if (smem_bytes > static_cast<size_t>(ctx->max_smem_optin))
         return set_error(SCIR_B200_ERR_UNSUPPORTED, "polyphase tile needs %zu B of shared memory", smem_bytes);
     auto kern = upfirdn_tile_kernel<UP, DOWN, G, KCP, Z, NCH>;
     static thread_local size_t configured[16] = {0};
-    if (smem_bytes > 48 * 1024 && configured[ctx->device & 15] < smem_bytes) {
+    if (smem_bytes > 48 * 1024 && configured[d] < smem_bytes) {
         SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)),
                   "cudaFuncSetAttribute(upfirdn_tile_kernel)");
-        configured[ctx->device & 15] = smem_bytes;
+        configured[d] = smem_bytes;
     }
     kern<<<static_cast<unsigned>(grid), kPolyNT, smem_bytes, ctx->stream>>>(q, taps);
     SCIR_CUDA(cudaGetLastError(), "upfirdn_tile_kernel launch");
@@ -188,25 +346,25 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
 
 // Z and NCH are runtime facts of the filter: dispatch onto the template grid.
 template <int UP, int DOWN, int G, int KCP, int Z>
-int launch_z(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid)
+int launch_z(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid, long long batch)
 {
-    if (nchunk == 1) return launch_one<UP, DOWN, G, KCP, Z, 1>(ctx, q, taps, nchunk, grid);
-    return launch_one<UP, DOWN, G, KCP, Z, 0>(ctx, q, taps, nchunk, grid);
+    if (nchunk == 1) return launch_one<UP, DOWN, G, KCP, Z, 1>(ctx, q, taps, nchunk, grid, batch);
+    return launch_one<UP, DOWN, G, KCP, Z, 0>(ctx, q, taps, nchunk, grid, batch);
 }
 
 template <int UP, int DOWN, int G, int KCP>
-int launch_rate(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, int z, long long grid)
+int launch_rate(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, int z, long long grid, long long batch)
 {
     if constexpr (UP >= 2) {
-        if (z == 1) return launch_z<UP, DOWN, G, KCP, 1>(ctx, q, taps, nchunk, grid);
+        if (z == 1) return launch_z<UP, DOWN, G, KCP, 1>(ctx, q, taps, nchunk, grid, batch);
     }
     if constexpr (UP >= 3) {
-        if (z == 2) return launch_z<UP, DOWN, G, KCP, 2>(ctx, q, taps, nchunk, grid);
+        if (z == 2) return launch_z<UP, DOWN, G, KCP, 2>(ctx, q, taps, nchunk, grid, batch);
     }
     if constexpr (UP >= 4) {
-        if (z == 3) return launch_z<UP, DOWN, G, KCP, 3>(ctx, q, taps, nchunk, grid);
+        if (z == 3) return launch_z<UP, DOWN, G, KCP, 3>(ctx, q, taps, nchunk, grid, batch);
     }
-    return launch_z<UP, DOWN, G, KCP, 0>(ctx, q, taps, nchunk, grid);
+    return launch_z<UP, DOWN, G, KCP, 0>(ctx, q, taps, nchunk, grid, batch);
 }
 
 struct RateGeom {
@@ -266,7 +424,7 @@ int launch_upfirdn_poly(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64
 
     int rc = SCIR_B200_OK;
 #define SCIR_RATE(U, D, GG) \
-    if (up == U && down == D) { rc = launch_rate<U, D, GG, KCP>(ctx, q, *tl, q.nchunk, z, grid); *handled = (rc == SCIR_B200_OK); return rc; }
+    if (up == U && down == D) { rc = launch_rate<U, D, GG, KCP>(ctx, q, *tl, q.nchunk, z, grid, batch); *handled = (rc == SCIR_B200_OK); return rc; }
     SCIR_RATE(3, 2, 10)
     SCIR_RATE(2, 3, 12)
     SCIR_RATE(2, 1, 12)
