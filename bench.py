@@ -9,9 +9,11 @@ N > 1: one process per GPU (torchrun), channels sharded across ranks, no data-pa
 (rows are independent); per-GPU work is fixed => weak scaling, value = all ranks' samples / max time.
 
 One JSON line is printed by rank 0.  Keys beyond the base contract:
-  roofline      algorithmic bytes of the dominant kernel / its CUDA-event launch time, against the
-                measured HBM peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback); `fp32` and
-                `shape_roofline` explain it: this kernel is FP32-issue bound, not HBM bound.
+  roofline      the dominant kernel against the roofline that bounds it.  HBM-bound launches (config 2 on
+                the tcgen05 Toeplitz kernel, config 4): algorithmic bytes / CUDA-event launch time against
+                the measured HBM peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback).  Tensor-bound
+                launches (configs 3, 5): executed tensor-pipe TFLOP/s against the measured dense-bf16 peak.
+                `tensor`, `fp32` and `shape_roofline` (BASELINE.md's max(bytes/HBM, 2K flops/FP32)) explain it.
   cpu_baseline  the CPU restatement of the reference loop (oracle/, kind "port") timed here on the
                 host cores over a bounded row sample.
   e2e           the same metric through the host-array C-ABI call (pinned host buffers, H2D+kernel+D2H
@@ -130,8 +132,8 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
 def run_step(cfg, signal_mod, gpu_mod, x, taps, out):
@@ -276,6 +278,7 @@ def main():
     sampler.sample()
     sampler.start()
     l0 = ctx.launch_count()
+    tc0 = ctx.get_option("toeplitz_launches")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -295,58 +298,120 @@ def main():
     value = outs * world / (ms_max * 1e-3) / 1e9
 
     # ---- per-kernel launch time for the roofline (events on the launching stream) -------------------
-    kern_ms = ms / max(launches / args.steps, 1) if cfg["op"] != "filtfilt" else ms
-    hbm_peak, peak_src = measured_peaks()
+    n_kern = max(launches / args.steps, 1)
+    kern_ms = ms / n_kern                                  # filtfilt: two launches of the same kernel per step
+    hbm_peak, peak_src, peaks = measured_peaks()
     ffma = C.c_double(0.0)
     L.lib().scir_b200_microbench_ffma(ctx.handle, 2000, C.byref(ffma))
+    tc_launches = ctx.get_option("toeplitz_launches") - tc0
+    tensor_path = tc_launches > 0
     achieved_gbs = abytes / (ms * 1e-3) / 1e9
     achieved_tf = aflops / (ms * 1e-3) / 1e12
-    t_roof = max(abytes / (hbm_peak * 1e9), aflops / (FP32_NOMINAL_TFLOPS * 1e12))
-    roofline = {
-        "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-        "traffic": TRAFFIC_PER_LAUNCH.get(args.config), "peak_source": peak_src, "kernel_ms": kern_ms,
-        "fp32": {"achieved_tflops": achieved_tf, "peak_nominal_tflops": FP32_NOMINAL_TFLOPS,
-                 "frac_nominal": achieved_tf / FP32_NOMINAL_TFLOPS, "peak_ffma_microbench_tflops": ffma.value,
-                 "frac_of_microbench": achieved_tf / ffma.value if ffma.value else None},
-        "shape_roofline": {"t_ms": t_roof * 1e3, "gsamples": outs / t_roof / 1e9, "frac": (t_roof * 1e3) / ms,
-                           "note": "max(bytes/measured HBM, flops/nominal FP32); this shape is FP32-issue bound"},
-    }
+    t_hbm = abytes / (hbm_peak * 1e9)
+    t_fp32 = aflops / (FP32_NOMINAL_TFLOPS * 1e12)
+    t_roof = max(t_hbm, t_fp32)
+    tensor = None
+    bound = "hbm"
+    if tensor_path:
+        # what the tcgen05 Toeplitz kernel executes: per 128 x 128 output tile, `terms` M128 N128 K16 MMAs for
+        # every K step of every Toeplitz block that meets a non-zero tap (fir_toeplitz.cu: issue_tile)
+        terms = opts.get("toeplitz_terms", 3)
+        k = cfg["k"]
+        pmax = (k - 1 + 127) // 128
+        ksteps = sum(8 - (max(0, 128 * pb - (k - 1)) >> 4) for pb in range(pmax + 1))
+        exec_flop_per_out = terms * ksteps * (2.0 * 128 * 128 * 16) / (128 * 128)
+        passes = 2 if cfg["op"] == "filtfilt" else 1
+        exec_tf = outs * passes * exec_flop_per_out / (ms * 1e-3) / 1e12
+        tc_peak = float(peaks.get("bf16_tflops", 2250.0))
+        t_tensor = outs * passes * exec_flop_per_out / (tc_peak * 1e12)
+        tensor = {"split": "fp16x%d block-scaled, fp32 accumulate in TMEM" % terms if not opts.get("toeplitz_split") else
+                           "bf16x%d, fp32 accumulate in TMEM" % terms,
+                  "executed_tflops": exec_tf, "peak_tflops": tc_peak,
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in peaks else "nominal 2250",
+                  "peak_sustained_tflops": peaks.get("bf16_tflops_sustained"),
+                  "frac_executed": exec_tf / tc_peak,
+                  "algorithmic_tflops": achieved_tf, "frac_algorithmic_x_terms": achieved_tf * terms / tc_peak,
+                  "mma_per_tile": terms * ksteps}
+        if t_tensor > t_hbm:
+            bound = "tensor"
+    if bound == "tensor":
+        roofline = {"bound": "tensor", "achieved": tensor["executed_tflops"], "peak": tensor["peak_tflops"], "unit": "TFLOP/s",
+                    "frac": tensor["frac_executed"], "traffic": TRAFFIC_PER_LAUNCH.get(args.config),
+                    "peak_source": tensor["peak_source"], "kernel_ms": kern_ms,
+                    "note": "achieved = tensor-pipe flops the kernel executes (split terms x K steps incl. block padding); "
+                            "algorithmic 2*K flop/output figures are in `tensor` and `fp32`",
+                    "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "frac": achieved_gbs / hbm_peak}}
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                    "traffic": TRAFFIC_PER_LAUNCH.get(args.config), "peak_source": peak_src, "kernel_ms": kern_ms}
+    roofline["tensor"] = tensor
+    roofline["fp32"] = {"achieved_tflops": achieved_tf, "peak_nominal_tflops": FP32_NOMINAL_TFLOPS,
+                        "frac_nominal": achieved_tf / FP32_NOMINAL_TFLOPS, "peak_ffma_microbench_tflops": ffma.value,
+                        "frac_of_microbench": achieved_tf / ffma.value if ffma.value else None,
+                        "note": "algorithmic 2*K flop/output against the CUDA-core FP32 peak; > 1 means the tensor path "
+                                "beat the FP32 roofline" if tensor_path else "direct-form FFMA kernel"}
+    roofline["shape_roofline"] = {"t_ms": t_roof * 1e3, "gsamples": outs / t_roof / 1e9, "frac": (t_roof * 1e3) / ms,
+                                  "note": "BASELINE.md per-shape roofline: max(bytes/measured HBM, 2*K flops/nominal FP32)"}
 
     # ---- e2e: host arrays through the C ABI (pinned buffers, H2D + kernel + D2H timed) ------------------
     e2e = None
-    if not args.no_e2e and cfg["op"] in ("fir", "lfilter"):
+    if not args.no_e2e:
         lib = L.lib()
-        nbytes = rows * n * 4
+        if cfg["op"] == "resample":
+            n_out = -(-n * cfg["up"] // cfg["down"])
+        else:
+            n_out = n
+        in_bytes, out_bytes = rows * n * 4, rows * n_out * 4
         hx, hy = C.c_void_p(), C.c_void_p()
-        rc1, rc2 = lib.scir_b200_host_alloc(nbytes, C.byref(hx)), lib.scir_b200_host_alloc(nbytes, C.byref(hy))
+        rc1, rc2 = lib.scir_b200_host_alloc(in_bytes, C.byref(hx)), lib.scir_b200_host_alloc(out_bytes, C.byref(hy))
         if rc1 == 0 and rc2 == 0:
             ax = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=(rows, n))
-            ay = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(rows, n))
+            ay = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(rows, n_out))
             ax[:] = x.cpu().numpy()
             hctx = gpu.Context(local_rank)
             for key, val in opts.items():
                 hctx.set_option(key, val)
-            order = L.TAPS_SCIR if cfg["op"] == "fir" else L.TAPS_LFILTER
+            fpp = C.POINTER(C.c_float)
+            tp = taps.ctypes.data_as(fpp)
+            xp, yp = C.cast(hx, fpp), C.cast(hy, fpp)
+            if cfg["op"] in ("fir", "lfilter"):
+                order = L.TAPS_SCIR if cfg["op"] == "fir" else L.TAPS_LFILTER
+                api = "scir_b200_fir1d_batched_f32_host"
+                call = lambda: lib.scir_b200_fir1d_batched_f32_host(hctx.handle, xp, n, tp, taps.size, order, yp, n_out, rows, n)
+            elif cfg["op"] == "resample":
+                api = "scir_b200_resample_poly_f32_host"
+                call = lambda: lib.scir_b200_resample_poly_f32_host(hctx.handle, tp, taps.size, cfg["up"], cfg["down"], xp, n,
+                                                                    rows, n, yp, n_out)
+            else:
+                api = "scir_b200_filtfilt_fir_f32_host"
+                call = lambda: lib.scir_b200_filtfilt_fir_f32_host(hctx.handle, tp, taps.size, L.PAD_ODD, -1, xp, n, yp, n_out,
+                                                                   rows, n)
             e_steps = max(3, min(args.steps, 10))
+            rc = 0
             for _ in range(2):
-                gpu.fir1d_batched_f32_cuda(ax, taps, ctx=hctx, out=ay, tap_order=order)
+                rc |= call()
             barrier()
             t0 = time.perf_counter()
             for _ in range(e_steps):
-                gpu.fir1d_batched_f32_cuda(ax, taps, ctx=hctx, out=ay, tap_order=order)
+                rc |= call()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / e_steps
             tt = torch.tensor([dt], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ok = bool(np.allclose(ay[:2], y[:2].cpu().numpy(), atol=1e-6))
-            e2e = {"value": outs * world / float(tt.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-                   "d2h_bytes_per_step": nbytes, "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps,
-                   "matches_device_path": ok, "api": "scir_b200_fir1d_batched_f32_host (pinned host buffers)"}
-            lib.scir_b200_host_free(hx)
-            lib.scir_b200_host_free(hy)
+            yd = y if not isinstance(y, np.ndarray) else torch.from_numpy(y)
+            ok = bool(rc == 0 and np.allclose(ay[:2], yd[:2].cpu().numpy(), atol=1e-6))
+            e2e = {"value": outs * world / float(tt.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                   "d2h_bytes_per_step": out_bytes, "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps,
+                   "matches_device_path": ok, "api": api + " (pinned host buffers; H2D, kernels and D2H inside the timed region)"}
+            if rc != 0:
+                e2e["error"] = L.last_error()
         else:
             e2e = {"value": None, "unit": UNIT, "error": L.last_error()}
+        if hx:
+            lib.scir_b200_host_free(hx)
+        if hy:
+            lib.scir_b200_host_free(hy)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None
@@ -372,7 +437,8 @@ def main():
                        "l2": "inputs larger than L2 (per-step working set >> 126 MB)" if abytes > 3e8 else
                              "working set fits L2 (latency/plumbing config)",
                        "variant": args.variant, "options": opts,
-                       "tensor_core_launches": ctx.get_option("toeplitz_launches")},
+                       "tensor_core_launches": int(tc_launches),
+                       "arithmetic": ("f32 in/out; " + tensor["split"]) if tensor else "f32 FFMA (CUDA cores)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -382,7 +448,12 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture of this command (profiles/); None until a capture exists for the config.
-TRAFFIC_PER_LAUNCH = {}
+TRAFFIC_PER_LAUNCH = {
+    "c2": 8.566e9,      # profiles/r01_c2_fir_toeplitz_kernel_v3.ncu.txt: 4.312 GB read + 4.254 GB written (algorithmic 8.590e9)
+    "c3": 8.544e9,      # profiles/r01_c3_fir_toeplitz_kernel.ncu.txt:    4.298 + 4.246            (algorithmic 8.590e9)
+    "c4": 21.451e9,     # profiles/r01_c4_upfirdn_stream_kernel.ncu.txt:  8.615 + 12.835           (algorithmic 21.475e9)
+    "c5": 17.229e9,     # profiles/r01_c5_fir_toeplitz_kernel.ncu.txt, per pass: 8.612 + 8.618     (algorithmic 17.180e9 per pass)
+}
 
 if __name__ == "__main__":
     main()

@@ -92,13 +92,26 @@ static int check_taps(const float* taps, int64_t k)
     return SCIR_B200_OK;
 }
 
-// Kernel choice for one FIR pass: the tcgen05 block-Toeplitz contraction for long filters (or when
-// forced), the FP32 direct family otherwise.
+// Kernel choice for one FIR pass, from measurements on B200 (profiles/README.md):
+//   * the FP32 direct family is FFMA-issue bound, time ~ K: at K = 63 it needs 2.40 ms for config 2 where
+//     the bytes alone take 1.31 ms;
+//   * the tcgen05 block-Toeplitz contraction (block-scaled FP16x3, error <= 3 * 2^-22 per product) runs the
+//     same launch in 1.54 ms and stays HBM-bound up to K ~ 130, so it takes over as soon as the direct
+//     kernel would leave the HBM roofline (K >= 48) -- provided the launch has at least one 128 x 128
+//     output tile per SM: below that its one-CTA-per-SM set-up (TMEM, Hankel tap arrays) is not amortised
+//     and the direct kernel's finer tiles win (config 1: 21 us vs 49 us);
+//   * long filters (K >= 1024) always take the tensor path: 17 ms vs the 118 ms FP32 roofline at K = 4097.
 int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
 {
     const int64_t mode = ctx->opt.long_tap_path;
-    const bool want = (mode == 2) || (mode == 0 && k >= ctx->opt.toeplitz_min_k);
-    if (want && ctx->opt.variant == 0 && toeplitz_supported(ctx, pass, k)) return launch_fir_toeplitz(ctx, pass, c, k);
+    if (mode != 1 && ctx->opt.variant == 0) {
+        int64_t tiles = 0;
+        if (toeplitz_supported(ctx, pass, k, &tiles)) {
+            const bool want = (mode == 2) || k >= ctx->opt.toeplitz_min_k ||
+                              (k >= ctx->opt.toeplitz_min_k_full && tiles >= ctx->sm_count);
+            if (want) return launch_fir_toeplitz(ctx, pass, c, k);
+        }
+    }
     return launch_fir_pass(ctx, pass, c, k);
 }
 
@@ -379,7 +392,10 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "upfirdn_variant")) return &o.upfirdn_variant;
     if (!strcmp(key, "toeplitz_terms")) return &o.toeplitz_terms;
     if (!strcmp(key, "toeplitz_split")) return &o.toeplitz_split;
+    if (!strcmp(key, "toeplitz_chains")) return &o.toeplitz_chains;
+    if (!strcmp(key, "toeplitz_ts")) return &o.toeplitz_ts;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
+    if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
     return nullptr;
 }

@@ -34,11 +34,14 @@ void clear_error();
 struct Options {
     int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
     int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
-    int64_t long_tap_path = 0;  // 0 auto (tensor path for k >= toeplitz_min_k); 1 force FP32 direct; 2 force tcgen05 Toeplitz
+    int64_t long_tap_path = 0;  // 0 auto (see launch_fir); 1 force FP32 direct; 2 force tcgen05 Toeplitz
     int64_t toeplitz_terms = 3; // split products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
     int64_t toeplitz_split = 0; // operand format of the split: 0 block-scaled FP16 (11-bit terms), 1 BF16 (8-bit terms)
+    int64_t toeplitz_chains = 1; // accumulation chains per tile in TMEM (2: consecutive MMAs alternate accumulators; measured: no gain)
+    int64_t toeplitz_ts = 1;     // 1: keep the first Toeplitz blocks in TMEM (A operand from TMEM); 0: all operands from shared memory
     int64_t toeplitz_loader = 0; // 0 auto (TMA-fed in-place buffers when they fit); 1 force the register-prefetch loader
-    int64_t toeplitz_min_k = 1024; // auto mode: smallest tap count routed to the tensor path
+    int64_t toeplitz_min_k = 1024; // auto mode: tap counts from here on always take the tensor path
+    int64_t toeplitz_min_k_full = 48; // auto mode: ... and from here on when the launch fills the GPU (>= 1 tile of 16384 outputs per SM)
     int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
 };
 
@@ -115,7 +118,7 @@ int launch_upfirdn(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up
                    int64_t ld_y, int64_t m_begin, int64_t m_count);
 
 // ---- long-tap tensor-core path (tcgen05 block-Toeplitz) -----------------------------------------
-bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k);
+bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles = nullptr);
 int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 
 int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);

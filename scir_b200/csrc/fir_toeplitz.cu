@@ -55,14 +55,13 @@ namespace {
 
 constexpr int TB = 128;                 // block length: MMA M, and the K extent of one p-block
 constexpr int TN = 128;                 // blocks (columns) per tile: MMA N
-constexpr int kEpiWarps = 4, kLoadWarps = 8;
+constexpr int kEpiWarps = 4, kLoadWarps = 16;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMmaWarp = kEpiWarps + kLoadWarps, kTmaWarp = kMmaWarp + 1;
 constexpr int kToepThreads = (kEpiWarps + kLoadWarps + 2) * 32;
-constexpr int kTmemCols = 2 * TN;       // two accumulator stages
 constexpr int kMaxBuf = 3;
 constexpr int kPmaxLimit = 32;
-constexpr int RMAX = ((TN + kPmaxLimit) * 16 + kLoadThreads - 1) / kLoadThreads;   // items (8 samples) per loader thread
+constexpr int RQMAX = ((TN + kPmaxLimit) * 32 + kLoadThreads - 1) / kLoadThreads;  // float4 chunks per loader thread
 
 enum { MODE_REGISTER = 0, MODE_INPLACE = 1 };
 enum { FMT_F16_SCALED = 0, FMT_BF16 = 1 };
@@ -87,6 +86,9 @@ struct ToepParams {
     int mode;                           // MODE_REGISTER / MODE_INPLACE
     int nbuf;                           // slab buffers: 3 in place, 1 or 2 in register mode
     int fmt;                            // FMT_F16_SCALED / FMT_BF16
+    int chains;                         // independent accumulation chains per tile (1 or 2): accumulators = 2 stages * chains * 128 columns
+    int ts_blocks;                      // Toeplitz blocks T_0 .. T_{ts_blocks-1} are kept in TMEM (A operand from TMEM)
+    int tmem_cols;                      // TMEM allocation (power of two): accumulators, then the A blocks
     int k;
     int hank_cores;                     // 16 * pmax + 31
     unsigned buf_bytes;                 // one buffer (multiple of 128)
@@ -139,6 +141,23 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t 
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
         : "memory");
 }
+// A operand from TMEM (lane = accumulator row, 16-bit K elements packed two per 32-bit column), B from shared memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& lo, const uint4& hi)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(lo.x), "r"(lo.y),
+                 "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -149,6 +168,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -195,81 +226,115 @@ __device__ __forceinline__ long long map_index(const FirPass& p, long long ip)
     return (p.dir > 0) ? ip : (p.n_v - 1 - ip);
 }
 
-// 8 consecutive samples -> one 16-byte core-matrix row per split term (hi | mid | lo), 16-bit each.
-template <bool F16>
-__device__ __forceinline__ void split_store(const float4& a, const float4& b, bool rev, float scale, int nver, uint32_t dst,
-                                            uint32_t ver_bytes)
+// 4 consecutive samples -> half of a 16-byte core-matrix row per split term (hi | mid | lo), 16-bit each.
+// `v` is in causal order already.
+template <bool F16, int NVER>
+__device__ __forceinline__ void split_store4(const float (&v)[4], float scale, uint32_t dst, uint32_t ver_bytes)
 {
-    float v[8];
-    v[0] = rev ? b.w : a.x; v[1] = rev ? b.z : a.y; v[2] = rev ? b.y : a.z; v[3] = rev ? b.x : a.w;
-    v[4] = rev ? a.w : b.x; v[5] = rev ? a.z : b.y; v[6] = rev ? a.y : b.z; v[7] = rev ? a.x : b.w;
-    uint32_t hi[4], mid[4], lo[4];
+    uint32_t hi[2], mid[2], lo[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 2; ++e) {
         if constexpr (F16) {
             const float s0 = v[2 * e] * scale, s1 = v[2 * e + 1] * scale;
             const __half2 h = __floats2half2_rn(s0, s1);
             const float r0 = s0 - __low2float(h), r1 = s1 - __high2float(h);
             const __half2 m = __floats2half2_rn(r0, r1);
-            const __half2 l = __floats2half2_rn(r0 - __low2float(m), r1 - __high2float(m));
             hi[e] = *reinterpret_cast<const uint32_t*>(&h);
             mid[e] = *reinterpret_cast<const uint32_t*>(&m);
-            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            if constexpr (NVER > 2) {
+                const __half2 l = __floats2half2_rn(r0 - __low2float(m), r1 - __high2float(m));
+                lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
         } else {
             const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
             const float r0 = v[2 * e] - __low2float(h), r1 = v[2 * e + 1] - __high2float(h);
             const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
-            const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
             hi[e] = *reinterpret_cast<const uint32_t*>(&h);
             mid[e] = *reinterpret_cast<const uint32_t*>(&m);
-            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            if constexpr (NVER > 2) {
+                const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - __low2float(m), r1 - __high2float(m));
+                lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
         }
     }
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ver_bytes), "r"(mid[0]), "r"(mid[1]), "r"(mid[2]), "r"(mid[3]) : "memory");
-    if (nver > 2)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * ver_bytes), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + ver_bytes), "r"(mid[0]), "r"(mid[1]) : "memory");
+    if constexpr (NVER > 2)
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + 2 * ver_bytes), "r"(lo[0]), "r"(lo[1]) : "memory");
 }
 
-__device__ __forceinline__ uint32_t absmax_bits(const float4& a, const float4& b)
+__device__ __forceinline__ uint32_t absmax_bits(const float4& a)
 {
     const uint32_t m0 = max(__float_as_uint(a.x) & 0x7fffffffu, __float_as_uint(a.y) & 0x7fffffffu);
     const uint32_t m1 = max(__float_as_uint(a.z) & 0x7fffffffu, __float_as_uint(a.w) & 0x7fffffffu);
-    const uint32_t m2 = max(__float_as_uint(b.x) & 0x7fffffffu, __float_as_uint(b.y) & 0x7fffffffu);
-    const uint32_t m3 = max(__float_as_uint(b.z) & 0x7fffffffu, __float_as_uint(b.w) & 0x7fffffffu);
-    return max(max(m0, m1), max(m2, m3));
+    return max(m0, m1);
 }
 
 // MMA issue for one tile: all P+1 Toeplitz blocks, every K=16 step that meets a non-zero tap, TERMS split
-// products each.  Run by the whole MMA warp with warp-uniform values; only the elected lane issues.
-template <int TERMS>
+// products each.  Run by the whole MMA warp with warp-uniform values; only the elected lane issues.  With
+// CHAINS = 2 consecutive MMAs alternate between two accumulators (summed in the epilogue), so that no MMA
+// waits on the accumulator its predecessor is still writing.
+template <int TERMS, int CHAINS>
 __device__ __forceinline__ void issue_tile(const ToepParams& q, bool leader, uint32_t dcol, uint32_t a_lo0, uint32_t x_lo0,
-                                           uint32_t hank16, uint32_t ver16, uint32_t idesc)
+                                           uint32_t hank16, uint32_t ver16, uint32_t idesc, uint32_t a_tmem0)
 {
-    uint32_t accum = 0;
+    constexpr uint32_t NVER = (TERMS == 6) ? 3u : 2u;
+    uint32_t idx = 0;
+    auto dst = [&]() { return (CHAINS == 2) ? (dcol + (idx & 1u) * TN) : dcol; };
+    auto acc = [&]() { return (idx >= static_cast<uint32_t>(CHAINS)) ? 1u : 0u; };
+    auto mma = [&](uint32_t a, uint32_t x) {              // both operands from shared memory
+        tc_mma(dst(), a, x, idesc, acc());
+        ++idx;
+    };
+    auto mma_ts = [&](uint32_t at, uint32_t x) {          // Toeplitz block from TMEM
+        tc_mma_ts(dst(), at, x, idesc, acc());
+        ++idx;
+    };
     const uint32_t two_cols = 2u * static_cast<uint32_t>(q.slab_cols);
     for (int pb = 0; pb <= q.pmax; ++pb) {
         const int ks0 = max(0, TB * pb - (q.k - 1)) >> 4;                // first K step with a non-zero tap in T_p
         uint32_t a = a_lo0 + 8u * static_cast<uint32_t>(16 * (q.pmax - pb) + 2 * ks0);
         uint32_t x = x_lo0 + static_cast<uint32_t>(ks0) * two_cols + static_cast<uint32_t>(q.pmax - pb);
-        for (int ks = ks0; ks < TB / 16; ++ks) {
-            if (leader) {
-                tc_mma(dcol, a, x, idesc, accum);                        // hi * hi
-                tc_mma(dcol, a, x + ver16, idesc, 1u);                   // hi * mid
-                tc_mma(dcol, a + hank16, x, idesc, 1u);                  // mid * hi
-                if constexpr (TERMS >= 4) tc_mma(dcol, a + hank16, x + ver16, idesc, 1u);
-                if constexpr (TERMS == 6) {
-                    tc_mma(dcol, a, x + 2u * ver16, idesc, 1u);          // hi * lo
-                    tc_mma(dcol, a + 2u * hank16, x, idesc, 1u);         // lo * hi
+        if (pb < q.ts_blocks) {
+            uint32_t at = a_tmem0 + static_cast<uint32_t>(pb) * NVER * 64u + static_cast<uint32_t>(ks0) * 8u;
+            for (int ks = ks0; ks < TB / 16; ++ks) {
+                if (leader) {
+                    mma_ts(at, x);                                       // hi * hi
+                    mma_ts(at, x + ver16);                               // hi * mid
+                    mma_ts(at + 64u, x);                                 // mid * hi
+                    if constexpr (TERMS >= 4) mma_ts(at + 64u, x + ver16);
+                    if constexpr (TERMS == 6) {
+                        mma_ts(at, x + 2u * ver16);                      // hi * lo
+                        mma_ts(at + 128u, x);                            // lo * hi
+                    }
+                } else {
+                    idx += TERMS;
                 }
+                at += 8u;
+                x += two_cols;
             }
-            accum = 1u;
-            a += 16u;
-            x += two_cols;
+        } else {
+            for (int ks = ks0; ks < TB / 16; ++ks) {
+                if (leader) {
+                    mma(a, x);                                           // hi * hi
+                    mma(a, x + ver16);                                   // hi * mid
+                    mma(a + hank16, x);                                  // mid * hi
+                    if constexpr (TERMS >= 4) mma(a + hank16, x + ver16);
+                    if constexpr (TERMS == 6) {
+                        mma(a, x + 2u * ver16);                          // hi * lo
+                        mma(a + 2u * hank16, x);                         // lo * hi
+                    }
+                } else {
+                    idx += TERMS;
+                }
+                a += 16u;
+                x += two_cols;
+            }
         }
     }
 }
 
+template <bool F16, int NVER>
 __global__ void __launch_bounds__(kToepThreads, 1)
 fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
 {
@@ -287,13 +352,14 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     const uint32_t smem0 = smem_u32(smem_raw);
     const uint32_t hank_bytes = static_cast<uint32_t>(q.hank_cores) * 128u;      // per version
     const uint32_t ver_bytes = 16u * static_cast<uint32_t>(q.slab_cols) * 16u;    // slab bytes per version
-    const uint32_t buf0_off = hank_bytes * static_cast<uint32_t>(q.nver);
+    const uint32_t buf0_off = hank_bytes * NVER;
     const uint32_t bar0 = smem_u32(&bars[0]);
     enum { RAW_FULL = 0, SLAB_FULL = kMaxBuf, BUF_EMPTY = 2 * kMaxBuf, ACC_FULL = 3 * kMaxBuf, ACC_EMPTY = 3 * kMaxBuf + 2 };
     auto BAR = [&](int which, int idx) { return bar0 + 8u * static_cast<uint32_t>(which + idx); };
     const int tile_cols = TN + q.pmax;
     const uint32_t raw_bytes = static_cast<uint32_t>(tile_cols) * TB * 4u;        // one fp32 tile incl. halo columns
-    const bool f16 = (q.fmt == FMT_F16_SCALED);
+    const uint32_t tmem_cols = static_cast<uint32_t>(q.tmem_cols);
+    const uint32_t a_col0 = 2u * TN * static_cast<uint32_t>(q.chains);             // A blocks follow the accumulators
     // a tile whose N + P columns are plain, aligned memory can be fetched by one bulk copy
     auto tile_lo = [&](long long ipA) { return (p.dir > 0) ? ipA : (p.n_v - ipA - static_cast<long long>(tile_cols) * TB); };
     auto tile_bulk = [&](long long ipA) {
@@ -315,7 +381,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         }
         fence_mbar_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_holder), kTmemCols);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_holder), tmem_cols);
     {
         // H[u][i][e] = g[8u + i + e],  g[w] = c[128 P + 127 - w]  (zero outside [0, k))
         const int top = TB * q.pmax + (TB - 1);
@@ -326,7 +392,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             const int ci = top - (8 * u + i + e);
             const float c = (ci >= 0 && ci < q.k) ? taps.c[ci] : 0.f;
             uint16_t h16, m16, l16;
-            if (f16) {
+            if constexpr (F16) {
                 const float cs = c * q.tap_scale;
                 const __half h = __float2half_rn(cs);
                 const float r1 = cs - __half2float(h);
@@ -342,7 +408,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             }
             H[idx] = h16;
             H[hank_elems + idx] = m16;
-            if (q.nver > 2) H[2 * hank_elems + idx] = l16;
+            if constexpr (NVER > 2) H[2 * hank_elems + idx] = l16;
         }
     }
     fence_proxy_async_smem();                              // H is read by the tensor core (async proxy)
@@ -350,6 +416,30 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_holder;
+    if (q.ts_blocks > 0) {
+        // The first Toeplitz blocks move into TMEM once (same Hankel aliasing, read with LDS.128): their MMAs
+        // then fetch only the signal operand from shared memory, which halves the tensor core's load on the
+        // shared-memory port -- the resource this kernel is bound by.
+        if (warp < kEpiWarps) {
+            const int rq = warp * 32 + lane;               // accumulator row r' = TMEM lane
+            const int mi = rq >> 3, i = rq & 7;
+            for (int pb = 0; pb < q.ts_blocks; ++pb)
+                for (int ver = 0; ver < NVER; ++ver)
+                    for (int ks = 0; ks < TB / 16; ++ks) {
+                        const unsigned char* src = smem_raw + static_cast<size_t>(ver) * hank_bytes +
+                                                   static_cast<size_t>(16 * (q.pmax - pb) + 2 * ks + mi) * 128 + i * 16;
+                        const uint4 lo = *reinterpret_cast<const uint4*>(src);          // K chunk 0: s = 16 ks + [0, 8)
+                        const uint4 hi = *reinterpret_cast<const uint4*>(src + 128);    // K chunk 1: s = 16 ks + [8, 16)
+                        tmem_st8(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a_col0 +
+                                     static_cast<uint32_t>((pb * NVER + ver) * 64 + ks * 8),
+                                 lo, hi);
+                    }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     const int ntiles = q.total_tiles;
     const int nbuf = q.nbuf;
@@ -375,39 +465,40 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         }
     } else if (warp >= kEpiWarps && warp < kEpiWarps + kLoadWarps) {
         // ===== LOADER / CONVERTER: stage the tile's N + P columns as split 16-bit core-matrix rows ============
-        // A thread owns items tl, tl + 256, ... (item = (column, 8-sample chunk)).
+        // A thread owns the float4 chunks tl, tl + 512, ... of the tile (chunk u = causal samples [4u, 4u+4) of
+        // the slab = half `u & 1` of core-matrix row (column u >> 5, K chunk (u >> 1) & 15)): lane-contiguous
+        // LDS.128 / LDG.128 in, conflict-free STS.64 out.
         const int tl = tid - kEpiWarps * 32;
         const int lw = tl >> 5;
-        const int nitems = tile_cols * 16;
+        const int nq = tile_cols * 32;
         const bool inplace = (q.mode == MODE_INPLACE);
-        float4 raw[RMAX][2];
-        uint32_t fastmask = 0;                             // items loaded in ascending memory order (anticausal: to be reversed)
+        float4 raw[RQMAX];
+        uint32_t fastmask = 0;                             // chunks held in ascending memory order (anticausal: to be reversed)
         uint32_t mx = 0;
-        // gather from global memory: fast aligned chunks by LDG.128, edge chunks rule by rule
+        // gather from global memory: aligned interior chunks by LDG.128, edge chunks rule by rule
         auto fetch = [&](int t) {
             const int row = t / q.tiles_per_row;
             const int ct = t - row * q.tiles_per_row;
-            const long long j0 = q.first_col + static_cast<long long>(ct) * TN;
+            const long long ipA = tile_ipA(ct);
             const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
             fastmask = 0;
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                const int item = tl + r * kLoadThreads;
-                if (item < nitems) {
-                    const int cidx = item >> 4, sc = item & 15;
-                    const long long ip0 = (j0 - q.pmax + cidx) * TB + sc * 8 - q.org;   // causal index of the chunk's first sample
-                    // virtual index of the chunk's lowest address: ip0 (causal) or n_v-1-ip0-7 (anticausal)
-                    const long long lo = (p.dir > 0) ? ip0 : (p.n_v - 8 - ip0);
-                    if (q.fast_ok && lo >= q.fast_lo && lo + 8 <= q.fast_hi) {
-                        raw[r][0] = *reinterpret_cast<const float4*>(xr + lo + p.in_off);
-                        raw[r][1] = *reinterpret_cast<const float4*>(xr + lo + p.in_off + 4);
+            for (int r = 0; r < RQMAX; ++r) {
+                const int u = tl + r * kLoadThreads;
+                if (u < nq) {
+                    const long long ip0 = ipA + 4 * u;                         // causal index of the chunk's first sample
+                    // virtual index of the chunk's lowest address: ip0 (causal) or n_v-1-ip0-3 (anticausal)
+                    const long long lo = (p.dir > 0) ? ip0 : (p.n_v - 4 - ip0);
+                    if (ip0 >= q.ip_hi) {                                      // newer than every wanted output: never read
+                        raw[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else if (q.fast_ok && lo >= q.fast_lo && lo + 4 <= q.fast_hi) {
+                        raw[r] = *reinterpret_cast<const float4*>(xr + lo + p.in_off);
                         fastmask |= 1u << r;
                     } else {                                                   // edge chunk: causal order, rule by rule
-                        float v[8];
+                        float v[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = tload(p, xr, (p.dir > 0) ? (ip0 + e) : (p.n_v - 1 - ip0 - e));
-                        raw[r][0] = make_float4(v[0], v[1], v[2], v[3]);
-                        raw[r][1] = make_float4(v[4], v[5], v[6], v[7]);
+                        for (int e = 0; e < 4; ++e) v[e] = tload(p, xr, (p.dir > 0) ? (ip0 + e) : (p.n_v - 1 - ip0 - e));
+                        raw[r] = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 }
             }
@@ -416,55 +507,62 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         auto gather_smem = [&](const float* rawt) {
             const int len = tile_cols * TB;
             const bool rev = p.dir < 0;
-            fastmask = rev ? 0xffffffffu : 0u;
+            fastmask = 0xffffffffu;
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                const int item = tl + r * kLoadThreads;
-                if (item < nitems) {
-                    const int o = item * 8;                                    // causal offset of the chunk in the tile
-                    const float* src = rev ? (rawt + (len - 8 - o)) : (rawt + o);
-                    raw[r][0] = *reinterpret_cast<const float4*>(src);
-                    raw[r][1] = *reinterpret_cast<const float4*>(src + 4);
-                }
+            for (int r = 0; r < RQMAX; ++r) {
+                const int u = tl + r * kLoadThreads;
+                if (u < nq) raw[r] = *reinterpret_cast<const float4*>(rev ? (rawt + (len - 4 - 4 * u)) : (rawt + 4 * u));
             }
         };
         auto local_max = [&]() {
             mx = 0;
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r)
-                if (tl + r * kLoadThreads < nitems) mx = max(mx, absmax_bits(raw[r][0], raw[r][1]));
+            for (int r = 0; r < RQMAX; ++r)
+                if (tl + r * kLoadThreads < nq) mx = max(mx, absmax_bits(raw[r]));
         };
         // block-wide max -> power-of-two scale (fmt 0); the named barrier doubles as the "everyone has
         // read the raw tile" point of the in-place conversion
         auto slab_scale = [&](int it) -> float {
-            if (!f16) {
+            if constexpr (!F16) {
                 if (inplace) asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
                 return 1.f;
+            } else {
+                const uint32_t wm = __reduce_max_sync(0xffffffffu, mx);
+                if (lane == 0) red_slots[it & 1][lw] = wm;
+                asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
+                uint32_t m = *(volatile uint32_t*)&red_slots[it & 1][lane & (kLoadWarps - 1)];
+                m = __reduce_max_sync(0xffffffffu, m);
+                // scale = 2^(141 - E): max|x| * scale in [2^14, 2^15); exponent field kept in [14, 253] so that
+                // both the scale and its inverse are normal numbers
+                const int e = static_cast<int>(m >> 23);
+                const int sexp = min(268 - e, 253);
+                if (tl == 0) inv_scale_ring[it & 7] = __uint_as_float(static_cast<uint32_t>(254 - sexp) << 23);
+                return __uint_as_float(static_cast<uint32_t>(sexp) << 23);
             }
-            const uint32_t wm = __reduce_max_sync(0xffffffffu, mx);
-            if (lane == 0) red_slots[it & 1][lw] = wm;
-            asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
-            uint32_t m = 0;
-#pragma unroll
-            for (int w = 0; w < kLoadWarps; ++w) m = max(m, *(volatile uint32_t*)&red_slots[it & 1][w]);
-            // scale = 2^(141 - E): max|x| * scale in [2^14, 2^15); exponent field kept in [14, 253] so that
-            // both the scale and its inverse are normal numbers
-            const int e = static_cast<int>(m >> 23);
-            const int sexp = min(268 - e, 253);
-            const float scale = __uint_as_float(static_cast<uint32_t>(sexp) << 23);
-            if (tl == 0) inv_scale_ring[it & 7] = __uint_as_float(static_cast<uint32_t>(254 - sexp) << 23);
-            return scale;
         };
         auto store_slab = [&](uint32_t sbase, float scale) {
+            const uint32_t row_bytes = static_cast<uint32_t>(q.slab_cols) * 16u;
+            if (p.dir > 0) {
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                const int item = tl + r * kLoadThreads;
-                if (item < nitems) {
-                    const int cidx = item >> 4, sc = item & 15;
-                    const bool rev = (p.dir < 0) && ((fastmask >> r) & 1u);
-                    const uint32_t dst = sbase + (static_cast<uint32_t>(sc) * q.slab_cols + cidx) * 16u;
-                    if (f16) split_store<true>(raw[r][0], raw[r][1], rev, scale, q.nver, dst, ver_bytes);
-                    else split_store<false>(raw[r][0], raw[r][1], rev, 1.f, q.nver, dst, ver_bytes);
+                for (int r = 0; r < RQMAX; ++r) {
+                    const int u = tl + r * kLoadThreads;
+                    if (u < nq) {
+                        const float v[4] = {raw[r].x, raw[r].y, raw[r].z, raw[r].w};
+                        const uint32_t dst = sbase + static_cast<uint32_t>((u >> 1) & 15) * row_bytes + static_cast<uint32_t>(u >> 5) * 16u + (u & 1) * 8u;
+                        split_store4<F16, NVER>(v, scale, dst, ver_bytes);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RQMAX; ++r) {
+                    const int u = tl + r * kLoadThreads;
+                    if (u < nq) {
+                        const bool rv = (fastmask >> r) & 1u;                  // ascending-memory chunks are time-reversed
+                        const float v[4] = {rv ? raw[r].w : raw[r].x, rv ? raw[r].z : raw[r].y, rv ? raw[r].y : raw[r].z,
+                                            rv ? raw[r].x : raw[r].w};
+                        const uint32_t dst = sbase + static_cast<uint32_t>((u >> 1) & 15) * row_bytes + static_cast<uint32_t>(u >> 5) * 16u + (u & 1) * 8u;
+                        split_store4<F16, NVER>(v, scale, dst, ver_bytes);
+                    }
                 }
             }
         };
@@ -489,7 +587,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         } else {
             // the thread's share of the NEXT tile is fetched into registers right after the current one is
             // stored, so the HBM latency is spent while the tensor core works and only the convert +
-            // STS.128 phase waits on buf_empty
+            // STS phase waits on buf_empty
             if (static_cast<int>(blockIdx.x) < ntiles) fetch(blockIdx.x);
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
                 local_max();
@@ -509,6 +607,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         const uint32_t a_lo0 = desc_lo(smem0, 128u);
         const uint32_t hank16 = hank_bytes >> 4, ver16 = ver_bytes >> 4;
         const uint32_t lbo_x = static_cast<uint32_t>(q.slab_cols) * 16u;
+        const uint32_t acc_cols = TN * static_cast<uint32_t>(q.chains);
         int it = 0, buf = 0;
         uint32_t par = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -518,13 +617,19 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             mbar_wait(BAR(SLAB_FULL, buf), par);
             tc_fence_after();
             const uint32_t x_lo0 = desc_lo(smem0 + buf0_off + static_cast<uint32_t>(buf) * q.buf_bytes, lbo_x);
-            const uint32_t dcol = tmem_base + static_cast<uint32_t>(acc * TN);
-            if (q.terms == 3) issue_tile<3>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc);
-            else if (q.terms == 4) issue_tile<4>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc);
-            else issue_tile<6>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc);
+            const uint32_t dcol = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
+            constexpr int T0 = (NVER > 2) ? 6 : 3;
+            const uint32_t a_tmem0 = tmem_base + a_col0;
+            if (q.chains == 2) {
+                if (NVER == 2 && q.terms == 4) issue_tile<4, 2>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc, a_tmem0);
+                else issue_tile<T0, 2>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc, a_tmem0);
+            } else {
+                if (NVER == 2 && q.terms == 4) issue_tile<4, 1>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc, a_tmem0);
+                else issue_tile<T0, 1>(q, leader, dcol, a_lo0, x_lo0, hank16, ver16, idesc, a_tmem0);
+            }
             if (leader) {
                 tc_commit(BAR(BUF_EMPTY, buf));            // buffer may be refilled once these MMAs retire
-                tc_commit(BAR(ACC_FULL, acc));             // accumulator complete
+                tc_commit(BAR(ACC_FULL, acc));             // accumulator(s) complete
             }
             __syncwarp();
             if (++buf == nbuf) { buf = 0; par ^= 1u; }
@@ -533,6 +638,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         // ===== EPILOGUE: TMEM -> registers -> coalesced row stores ==========================================
         int it = 0;
         const int rr = TB - 1 - (warp * 32 + lane);        // accumulator rows are reversed (Hankel trick)
+        const uint32_t acc_cols = TN * static_cast<uint32_t>(q.chains);
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t apar = (it >> 1) & 1;
@@ -543,14 +649,25 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             mbar_wait(BAR(ACC_FULL, acc), apar);
             tc_fence_after();
             // un-scale: exact powers of two (1 in BF16 mode); written by the loaders long before ACC_FULL
-            const float inv_x = f16 ? *(volatile float*)&inv_scale_ring[it & 7] : 1.f;
+            const float inv_x = F16 ? *(volatile float*)&inv_scale_ring[it & 7] : 1.f;
             const float inv_c = q.tap_inv;
             const long long ip_first = j0 * TB - q.org, ip_last = (j0 + TN) * TB - q.org;      // this tile's outputs [first, last)
             const bool interior = ip_first >= q.ip_lo && ip_last <= q.ip_hi;
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc) * acc_cols;
 #pragma unroll 1
             for (int c4 = 0; c4 < TN / 32; ++c4) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * TN + c4 * 32), v);
+                tmem_ld32(tbase + static_cast<uint32_t>(c4 * 32), v);
+                if (q.chains == 2) {                       // second accumulation chain
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t w[16];
+                        tmem_ld16(tbase + static_cast<uint32_t>(TN + c4 * 32 + hh * 16), w);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            v[hh * 16 + c] = __float_as_uint(__uint_as_float(v[hh * 16 + c]) + __uint_as_float(w[c]));
+                    }
+                }
                 const long long ipb = (j0 + c4 * 32) * TB + rr - q.org;
                 if (interior) {                            // one base pointer, immediate offsets, no guards
                     float* yb = yr + map_index(p, ipb);
@@ -578,7 +695,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -602,6 +719,16 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
     if (terms != 3 && terms != 4 && terms != 6) terms = 3;
     q.terms = static_cast<int>(terms);
     q.nver = (terms == 6) ? 3 : 2;
+    q.chains = (ctx->opt.toeplitz_chains == 2) ? 2 : 1;
+    {   // TMEM: 2 accumulator stages x chains x 128 columns, then as many Toeplitz blocks (64 columns per split term)
+        // as fit in the 512 columns; blocks beyond that stay shared-memory operands
+        const int acc_cols = 2 * TN * q.chains;
+        const int room = (512 - acc_cols) / (64 * q.nver);
+        q.ts_blocks = (ctx->opt.toeplitz_ts == 0) ? 0 : std::min(q.pmax + 1, room);
+        const int need = acc_cols + q.ts_blocks * 64 * q.nver;
+        q.tmem_cols = 32;
+        while (q.tmem_cols < need) q.tmem_cols *= 2;
+    }
     const size_t hank = static_cast<size_t>(q.hank_cores) * 128 * q.nver;
     const size_t slab = static_cast<size_t>(16) * q.slab_cols * 16 * q.nver;
     const size_t raw = static_cast<size_t>(TN + q.pmax) * TB * 4;
@@ -660,10 +787,12 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
 
 }  // namespace
 
-bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k)
+bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles)
 {
     ToepPlan plan;
-    return pass.batch > 0 && pass.out_end > pass.out_begin && make_plan(ctx, pass, nullptr, k, &plan);
+    if (!(pass.batch > 0 && pass.out_end > pass.out_begin && make_plan(ctx, pass, nullptr, k, &plan))) return false;
+    if (tiles) *tiles = plan.q.total_tiles;
+    return true;
 }
 
 int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
@@ -676,16 +805,21 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
     thread_local ToepTaps* tl = nullptr;
     if (!tl) tl = new ToepTaps();
     for (int i = 0; i < SCIR_B200_MAX_TAPS; ++i) tl->c[i] = (i < k) ? c[i] : 0.f;
-    static thread_local size_t configured[16] = {};
+    using Kern = void (*)(const ToepParams, const ToepTaps);
+    const bool f16 = (plan.q.fmt == FMT_F16_SCALED);
+    const int flavour = (f16 ? 0 : 2) + (plan.q.nver > 2 ? 1 : 0);
+    const Kern kerns[4] = {fir_toeplitz_kernel<true, 2>, fir_toeplitz_kernel<true, 3>, fir_toeplitz_kernel<false, 2>,
+                           fir_toeplitz_kernel<false, 3>};
+    const Kern kern = kerns[flavour];
+    static thread_local size_t configured[16][4] = {};
     const int d = ctx->device & 15;
-    if (configured[d] < plan.smem_bytes) {
-        SCIR_CUDA(cudaFuncSetAttribute(fir_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(plan.smem_bytes)),
+    if (configured[d][flavour] < plan.smem_bytes) {
+        SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)),
                   "cudaFuncSetAttribute(fir_toeplitz_kernel)");
-        configured[d] = plan.smem_bytes;
+        configured[d][flavour] = plan.smem_bytes;
     }
     const int grid = std::min(plan.q.total_tiles, ctx->sm_count);
-    fir_toeplitz_kernel<<<grid, kToepThreads, plan.smem_bytes, ctx->stream>>>(plan.q, *tl);
+    kern<<<grid, kToepThreads, plan.smem_bytes, ctx->stream>>>(plan.q, *tl);
     SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
     ctx->launches++;
     ctx->toeplitz_launches++;

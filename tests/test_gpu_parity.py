@@ -199,12 +199,21 @@ def test_impulse_linearity_and_dc_properties_at_scale():
     pos = [0, 5119, 5120, n - 1]
     for r, p in enumerate(pos):
         x[r, p] = 1.0
-    y = gpu.fir1d_batched_f32_cuda(x, taps).cpu().numpy()
+    direct = gpu.Context(0)
+    direct.set_option("long_tap_path", 1)                  # FP32 direct family
+    y = gpu.fir1d_batched_f32_cuda(x, taps, ctx=direct)
+    direct.sync()
+    y = y.cpu().numpy()
+    # the launch fills the GPU, so auto dispatch takes the tcgen05 path: taps are reproduced to the split's
+    # 22 bits (x = 1 is exact in FP16, c = ch + cm + O(2^-22 c)), far inside the path's tolerance
+    yt = gpu.fir1d_batched_f32_cuda(x, taps).cpu().numpy()
     for r, p in enumerate(pos):
         want = np.zeros(n, np.float32)
         seg = b[: max(0, min(k, n - p))]
         want[p:p + seg.size] = seg
         assert np.array_equal(y[r], want), r               # exact: one product per output
+        assert np.abs(yt[r] - want).max() <= 2.0 ** -21 * np.abs(b).max(), r
+        assert np.array_equal(yt[r] != 0, want != 0) or np.abs(yt[r][want == 0]).max() == 0.0
     g = torch.Generator(device="cuda").manual_seed(42)
     a = torch.rand((8, n), device="cuda", generator=g) * 2 - 1
     c = torch.rand((8, n), device="cuda", generator=g) * 2 - 1

@@ -122,6 +122,23 @@ def test_toeplitz_filtfilt_matches_direct_and_oracle(padtype, loader):
     assert np.abs(yz - O.filtfilt_fir_nopad(b, x)).max() <= tol(hc, x) * 2
 
 
+@pytest.mark.parametrize("k", [63, 300, 4097])
+@pytest.mark.parametrize("loader", [0, 1])
+def test_toeplitz_single_accumulation_chain(k, loader):
+    """toeplitz_chains=1 (one TMEM accumulator per tile instead of two alternating ones) is the A/B switch
+    for the MMA dependency experiment; both settings must give the same answer to rounding."""
+    rng = np.random.RandomState(k)
+    x = (rng.rand(3, 50000).astype(np.float32) * 2 - 1)
+    taps = rng.randn(k).astype(np.float32)
+    want = O.fir1d_batched_f32_acc64(x, taps)
+    for chains, ts in ((1, 1), (2, 1), (1, 0), (2, 0)):
+        ctx = toep_ctx(3, loader, 0)
+        ctx.set_option("toeplitz_chains", chains)
+        ctx.set_option("toeplitz_ts", ts)          # 1: first Toeplitz blocks as TMEM operands, 0: all from shared memory
+        y = run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=ctx)).cpu().numpy()
+        assert np.abs(y - want).max() <= tol(taps, x), (chains, ts)
+
+
 def test_toeplitz_many_tiles_and_views():
     """More tiles than SMs (persistent CTAs wrap both pipelines), unaligned rows (scalar loader path)."""
     rng = np.random.RandomState(3)

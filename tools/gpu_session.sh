@@ -41,10 +41,10 @@ PY
   done
 fi
 if has toepbench; then
-  for spec in "c3 long_tap_path=2" "c3 toeplitz_split=1 toeplitz_terms=3" "c3 toeplitz_terms=4" \
-              "c5 long_tap_path=2" "c5 long_tap_path=2 toeplitz_loader=1" "c5 long_tap_path=2 toeplitz_split=1" \
-              "c2 long_tap_path=2" "c2 long_tap_path=2 toeplitz_loader=1" "c2 long_tap_path=2 toeplitz_split=1" \
-              "c2 long_tap_path=2 toeplitz_terms=4" "c1 long_tap_path=2"; do
+  for spec in "c3 long_tap_path=2" "c3 toeplitz_ts=0" \
+              "c5 long_tap_path=2" "c5 toeplitz_ts=0" "c5 toeplitz_loader=1" \
+              "c2 long_tap_path=2" "c2 toeplitz_ts=0" "c2 toeplitz_loader=1" "c2 toeplitz_split=1" "c2 toeplitz_terms=4" \
+              "c2 long_tap_path=1" "c5 long_tap_path=1"; do
     set -- $spec; cfg=$1; shift; o=""; tag=$cfg; for kv in "$@"; do o="$o --opt $kv"; tag="${tag}_${kv%%=*}${kv#*=}"; done
     timeout 300 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu --no-e2e $o > $OUT/benchT_$tag.json 2> $OUT/benchT_$tag.err
     python -c "import json; d=json.load(open('$OUT/benchT_$tag.json')); print('$spec ->', round(d['value'],2), 'Gs/s', round(d['ms_per_step'],3), 'ms', 'tc_launches', d['config'].get('tensor_core_launches'))" || tail -5 $OUT/benchT_$tag.err
@@ -55,6 +55,10 @@ if has ncu_toep; then
      python bench.py --config c3 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_c3_toeplitz.log 2>&1; echo "ncu toeplitz c3 rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_toeplitz -s 3 -c 1 -f -o $OUT/prof_c2_toeplitz \
      python bench.py --config c2 --opt long_tap_path=2 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_c2_toeplitz.log 2>&1; echo "ncu toeplitz c2 rc=$?"
+fi
+if has ncu_toep_c5; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_toeplitz -s 6 -c 2 -f -o $OUT/prof_c5_toeplitz \
+     python bench.py --config c5 --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_c5_toeplitz.log 2>&1; echo "ncu toeplitz c5 rc=$?"
 fi
 if has ncu_toep_c2; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fir_toeplitz -s 3 -c 1 -f -o $OUT/prof_c2_toeplitz \
