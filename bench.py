@@ -60,10 +60,14 @@ CONFIGS = {
     "c3": dict(rows=256, n=1 << 22, k=4097, op="lfilter", desc="long-tap FIR 256x2^22, 4097 taps"),
     "c4": dict(rows=2048, n=1 << 20, k=96, op="resample", up=3, down=2, desc="resample_poly 3/2, 2048x2^20, Kaiser 96"),
     "c5": dict(rows=8192, n=1 << 18, k=255, op="filtfilt", desc="filtfilt FIR 255 taps, 8192x2^18, odd pad"),
+    # SURVEY 8(f).1 (not a BASELINE config): DeviceArray add_scalar_auto on device-resident data, 2^30 elements
+    "e1": dict(rows=1024, n=1 << 20, k=1, op="ew", desc="DeviceArray add_scalar_auto, 2^30 f32 elements (8 B/element)"),
 }
 
 
 def make_taps(cfg):
+    if cfg["op"] == "ew":
+        return np.asarray([1.5], np.float32)
     if cfg["op"] == "fir":
         return (1.0 / (np.arange(cfg["k"], dtype=np.float32) + 1.0)).astype(np.float32)      # fir_bench.rs:14-18
     if cfg["op"] == "lfilter":
@@ -138,6 +142,13 @@ def measured_peaks():
 
 def run_step(cfg, signal_mod, gpu_mod, x, taps, out):
     op = cfg["op"]
+    if op == "ew":
+        from scir_b200 import _lib as L
+        ctx = gpu_mod.torch_context(x)
+        rc = L.lib().scir_b200_add_scalar_f32(ctx.handle, C.c_void_p(x.data_ptr()), float(taps[0]), C.c_void_p(out.data_ptr()),
+                                              x.numel())
+        assert rc == 0, L.last_error()
+        return out
     if op == "fir":
         return gpu_mod.fir1d_batched_f32_cuda(x, taps, out=out)
     if op == "lfilter":
@@ -258,7 +269,7 @@ def main():
     assert r1 - r0 == rows
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     x = torch.rand((rows, n), device=dev, generator=g) * 2 - 1
-    out = torch.empty_like(x) if cfg["op"] in ("fir", "lfilter") else None
+    out = torch.empty_like(x) if cfg["op"] in ("fir", "lfilter", "ew") else None
     ctx = gpu.torch_context(x)
     if args.variant:
         ctx.set_option("variant", args.variant)
@@ -355,7 +366,7 @@ def main():
 
     # ---- e2e: host arrays through the C ABI (pinned buffers, H2D + kernel + D2H timed) ------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and cfg["op"] != "ew":
         lib = L.lib()
         if cfg["op"] == "resample":
             n_out = -(-n * cfg["up"] // cfg["down"])
@@ -415,7 +426,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and cfg["op"] != "ew":
         eff, ctaps = cfg, taps
         if cfg["op"] == "resample":
             eff = dict(cfg, k=cfg["k"] // cfg["up"], op="lfilter")

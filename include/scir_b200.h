@@ -170,6 +170,14 @@ SCIR_B200_API int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx *ctx,
                                     float *h_y, int64_t ld_y,
                                     int64_t batch, int64_t n);
 
+/* ---- DeviceArray<f32> elementwise ops on device-resident data -----------------
+ * Replace add_scalar_f32_cuda / mul_scalar_f32_cuda / add_vec_f32_cuda (lib.rs:912-1034, 840-911), the
+ * Device::Cuda arms of add_scalar_auto / mul_scalar_auto / add_auto (lib.rs:268-377).  n elements, any
+ * alignment; y may alias a (and b).  Bit-identical to the CPU loops lib.rs:206-255 (one add or mul, no FMA). */
+SCIR_B200_API int scir_b200_add_scalar_f32(scir_b200_ctx *ctx, const float *d_a, float alpha, float *d_y, int64_t n);
+SCIR_B200_API int scir_b200_mul_scalar_f32(scir_b200_ctx *ctx, const float *d_a, float alpha, float *d_y, int64_t n);
+SCIR_B200_API int scir_b200_add_f32(scir_b200_ctx *ctx, const float *d_a, const float *d_b, float *d_y, int64_t n);
+
 /* ---- multi-GPU front end: rows (channels) sharded across devices, no collective --- */
 SCIR_B200_API int scir_b200_mg_create(const int *devices, int n_devices, scir_b200_mg **mg);
 SCIR_B200_API int scir_b200_mg_destroy(scir_b200_mg *mg);

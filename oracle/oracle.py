@@ -192,3 +192,22 @@ def filtfilt_fir(b, x, padtype=PAD_ODD, padlen=-1):
     if rc != 0:
         raise ValueError("The length of the input vector x must be greater than padlen")
     return y
+
+
+# ---- DeviceArray elementwise ops (crates/scir-gpu/src/lib.rs:206-255): one IEEE f32 op per element ----------
+def add_scalar_f32(a, alpha):
+    """lib.rs:206-212 (`*v += alpha`)."""
+    return (np.asarray(a, np.float32) + np.float32(alpha)).astype(np.float32)
+
+
+def mul_scalar_f32(a, alpha):
+    """lib.rs:223-229 (`*v *= alpha`)."""
+    return (np.asarray(a, np.float32) * np.float32(alpha)).astype(np.float32)
+
+
+def add_f32(a, b):
+    """lib.rs:245-254 (`*o += *r`); shapes must match (ShapeMismatch)."""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    if a.shape != b.shape:
+        raise ValueError("ShapeMismatch")
+    return (a + b).astype(np.float32)

@@ -58,6 +58,9 @@ SIGNATURES = {
     "scir_b200_resample_poly_f32_host": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64]),
     "scir_b200_filtfilt_fir_f32": (C.c_int, [vp, fp, i64, C.c_int, i64, fp, i64, fp, i64, i64, i64]),
     "scir_b200_filtfilt_fir_f32_host": (C.c_int, [vp, fp, i64, C.c_int, i64, fp, i64, fp, i64, i64, i64]),
+    "scir_b200_add_scalar_f32": (C.c_int, [vp, fp, C.c_float, fp, i64]),
+    "scir_b200_mul_scalar_f32": (C.c_int, [vp, fp, C.c_float, fp, i64]),
+    "scir_b200_add_f32": (C.c_int, [vp, fp, fp, fp, i64]),
     "scir_b200_mg_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
     "scir_b200_mg_destroy": (C.c_int, [vp]),
     "scir_b200_mg_device_count": (C.c_int, [vp, C.POINTER(C.c_int)]),

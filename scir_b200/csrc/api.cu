@@ -243,20 +243,32 @@ static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int
         float* din = static_cast<float*>(ctx->stage_in[s].ptr);
         float* dout = static_cast<float*>(ctx->stage_out[s].ptr);
         if (blk >= 3) SCIR_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
-        if (n_in > 0)
-            SCIR_CUDA(cudaMemcpy2DAsync(din, ldi * 4, h_x + r0 * ld_x, ld_x * 4, n_in * 4, nr,
-                                        cudaMemcpyHostToDevice, ctx->s_h2d),
-                      "cudaMemcpy2DAsync(H2D)");
+        if (n_in > 0) {
+            if (ld_x == n_in && ldi == n_in)               // dense rows: one linear DMA
+                SCIR_CUDA(cudaMemcpyAsync(din, h_x + r0 * ld_x, static_cast<size_t>(nr) * n_in * 4, cudaMemcpyHostToDevice,
+                                          ctx->s_h2d),
+                          "cudaMemcpyAsync(H2D)");
+            else
+                SCIR_CUDA(cudaMemcpy2DAsync(din, ldi * 4, h_x + r0 * ld_x, ld_x * 4, n_in * 4, nr,
+                                            cudaMemcpyHostToDevice, ctx->s_h2d),
+                          "cudaMemcpy2DAsync(H2D)");
+        }
         SCIR_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->s_h2d), "cudaEventRecord");
         SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0), "cudaStreamWaitEvent");
         if (blk >= 3) SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0), "cudaStreamWaitEvent");
         SCIR_TRY(fn(nr, din, ldi, dout, ldo));
         SCIR_CUDA(cudaEventRecord(ctx->ev_k[s], ctx->stream), "cudaEventRecord");
         SCIR_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
-        if (n_out > 0)
-            SCIR_CUDA(cudaMemcpy2DAsync(h_y + r0 * ld_y, ld_y * 4, dout, ldo * 4, n_out * 4, nr,
-                                        cudaMemcpyDeviceToHost, ctx->s_d2h),
-                      "cudaMemcpy2DAsync(D2H)");
+        if (n_out > 0) {
+            if (ld_y == n_out && ldo == n_out)
+                SCIR_CUDA(cudaMemcpyAsync(h_y + r0 * ld_y, dout, static_cast<size_t>(nr) * n_out * 4, cudaMemcpyDeviceToHost,
+                                          ctx->s_d2h),
+                          "cudaMemcpyAsync(D2H)");
+            else
+                SCIR_CUDA(cudaMemcpy2DAsync(h_y + r0 * ld_y, ld_y * 4, dout, ldo * 4, n_out * 4, nr,
+                                            cudaMemcpyDeviceToHost, ctx->s_d2h),
+                          "cudaMemcpy2DAsync(D2H)");
+        }
         SCIR_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->s_d2h), "cudaEventRecord");
     }
     SCIR_CUDA(cudaStreamSynchronize(ctx->s_d2h), "cudaStreamSynchronize(D2H)");
@@ -630,6 +642,39 @@ int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx* ctx, const float* b, int64_t 
                          [&](int64_t nr, const float* din, int64_t ldi, float* dout, int64_t ldo) {
                              return filtfilt_device(ctx, b, k, pad_mode, padlen, din, ldi, dout, ldo, nr, n);
                          });
+}
+
+// ---- DeviceArray elementwise ops on device-resident f32 (lib.rs:268-377 dispatch, :840-1034 CUDA wrappers) ----
+static int check_vec(const void* p, int64_t n, const char* name)
+{
+    if (n < 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "%s: negative length", name);
+    if (n > 0 && p == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "%s is NULL", name);
+    return SCIR_B200_OK;
+}
+
+int scir_b200_add_scalar_f32(scir_b200_ctx* ctx, const float* d_a, float alpha, float* d_y, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_vec(d_a, n, "a"));
+    SCIR_TRY(check_vec(d_y, n, "y"));
+    return launch_elementwise(ctx, 0, d_a, nullptr, alpha, d_y, n);
+}
+
+int scir_b200_mul_scalar_f32(scir_b200_ctx* ctx, const float* d_a, float alpha, float* d_y, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_vec(d_a, n, "a"));
+    SCIR_TRY(check_vec(d_y, n, "y"));
+    return launch_elementwise(ctx, 1, d_a, nullptr, alpha, d_y, n);
+}
+
+int scir_b200_add_f32(scir_b200_ctx* ctx, const float* d_a, const float* d_b, float* d_y, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    SCIR_TRY(check_vec(d_a, n, "a"));
+    SCIR_TRY(check_vec(d_b, n, "b"));
+    SCIR_TRY(check_vec(d_y, n, "y"));
+    return launch_elementwise(ctx, 2, d_a, d_b, 0.f, d_y, n);
 }
 
 int scir_b200_shard_rows(int64_t batch, int world, int rank, int64_t* row_begin, int64_t* row_end)

@@ -123,6 +123,9 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
 
 int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);
 
+// ---- DeviceArray elementwise ops (elementwise.cu): op 0 add-scalar, 1 mul-scalar, 2 add ------------------
+int launch_elementwise(scir_b200_ctx* ctx, int op, const float* d_a, const float* d_b, float alpha, float* d_y, int64_t n);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace scir_b200

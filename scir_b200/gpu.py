@@ -260,6 +260,47 @@ class DeviceArray:
             self._fin()
             self._dptr, self._device = None, Device.Cpu
 
+    # ---- elementwise ops with device dispatch (lib.rs:268-377) -------------------------------------------
+    def _new_like(self) -> "DeviceArray":
+        lib = _load()
+        out = DeviceArray(self._shape, self._dtype, np.empty(0, np.float32))
+        p = C.c_void_p()
+        _check(lib.scir_b200_malloc(self._ctx.handle, max(self._host.size * 4, 4), C.byref(p)))
+        out._dptr, out._device, out._ctx = p, Device.Cuda, self._ctx
+        out._host = np.empty(self._host.size, np.float32)
+        out._fin = weakref.finalize(out, lib.scir_b200_free, self._ctx.handle, p)
+        return out
+
+    def _need_cuda(self, what):
+        if self._device != Device.Cuda:
+            raise GpuError.backend_unavailable(
+                f"{what}: Device.Cpu arrays are served by the reference crate's own CPU loops (lib.rs:206-255); "
+                "scir_b200 is the CUDA backend and has no CPU path")
+
+    def add_scalar_auto(self, alpha: float) -> "DeviceArray":
+        """lib.rs:268-301, Device::Cuda arm (add_scalar_f32_cuda :912-972) on device-resident data."""
+        self._need_cuda("add_scalar_auto")
+        out = self._new_like()
+        _check(_load().scir_b200_add_scalar_f32(self._ctx.handle, self._dptr, float(alpha), out._dptr, self._host.size))
+        return out
+
+    def mul_scalar_auto(self, alpha: float) -> "DeviceArray":
+        """lib.rs:355-388, Device::Cuda arm (mul_scalar_f32_cuda :974-1034)."""
+        self._need_cuda("mul_scalar_auto")
+        out = self._new_like()
+        _check(_load().scir_b200_mul_scalar_f32(self._ctx.handle, self._dptr, float(alpha), out._dptr, self._host.size))
+        return out
+
+    def add_auto(self, other: "DeviceArray") -> "DeviceArray":
+        """lib.rs:303-353: shapes must match (ShapeMismatch :304-306), both arrays on the same device."""
+        if self._shape != other._shape:
+            raise GpuError.shape_mismatch("add_auto: shapes differ")
+        self._need_cuda("add_auto")
+        other._need_cuda("add_auto")
+        out = self._new_like()
+        _check(_load().scir_b200_add_f32(self._ctx.handle, self._dptr, other._dptr, out._dptr, self._host.size))
+        return out
+
     def fir1d_batched(self, taps, tap_order: int = L.TAPS_SCIR) -> "DeviceArray":
         """Device-resident FIR: no PCIe traffic when chaining."""
         if self._device != Device.Cuda or len(self._shape) != 2:

@@ -534,6 +534,60 @@ def test_device_array_roundtrip_and_chained_fir():
 
 
 # ---- multi-GPU front end (needs >= 2 devices) ------------------------------------------------------------
+def test_device_array_elementwise_ops_bit_exact():
+    """add_scalar_auto / mul_scalar_auto / add_auto (lib.rs:268-377) on device-resident arrays: the reference's
+    doc-test vectors (lib.rs:258-262, :293-298, :345-350), then random data of awkward lengths bit-exact against
+    the CPU loops, chained without leaving the device."""
+    a = gpu.DeviceArray.from_cpu_slice([3], gpu.DType.F32, [1.0, 2.0, 3.0])
+    a.to_device(Device.Cuda)
+    assert a.add_scalar_auto(1.0).to_cpu_vec() == [2.0, 3.0, 4.0]
+    assert a.mul_scalar_auto(2.0).to_cpu_vec() == [2.0, 4.0, 6.0]
+    b = gpu.DeviceArray.from_cpu_slice([3], gpu.DType.F32, [0.5, 1.5, 2.5])
+    b.to_device(Device.Cuda)
+    assert a.add_auto(b).to_cpu_vec() == [1.5, 3.5, 5.5]
+    c = gpu.DeviceArray.from_cpu_slice([2], gpu.DType.F32, [1.0, 2.0])
+    c.to_device(Device.Cuda)
+    with pytest.raises(gpu.GpuError) as ei:
+        a.add_auto(c)
+    assert ei.value.kind == "ShapeMismatch"
+    cpu = gpu.DeviceArray.from_cpu_slice([3], gpu.DType.F32, [1.0, 2.0, 3.0])
+    with pytest.raises(gpu.GpuError):                       # no CPU path in this backend
+        cpu.add_scalar_auto(1.0)
+    rng = np.random.RandomState(9)
+    for n in (1, 3, 4, 1023, 4096 * 4 * 4 + 5, 3_000_001):
+        x = (rng.randn(n) * 10).astype(np.float32)
+        z = (rng.randn(n) * 1e-3).astype(np.float32)
+        dx = gpu.DeviceArray.from_cpu_slice([n], gpu.DType.F32, x)
+        dz = gpu.DeviceArray.from_cpu_slice([n], gpu.DType.F32, z)
+        dx.to_device(Device.Cuda)
+        dz.to_device(Device.Cuda)
+        got = dx.mul_scalar_auto(1.7).add_scalar_auto(-0.3).add_auto(dz)          # stays in HBM between ops
+        want = O.add_f32(O.add_scalar_f32(O.mul_scalar_f32(x, 1.7), -0.3), z)
+        assert np.array_equal(np.asarray(got.to_cpu_vec(), np.float32), want), n
+
+
+def test_elementwise_unaligned_views_and_aliasing():
+    lib = L.lib()
+    ctx = gpu.Context(0)
+    rng = np.random.RandomState(10)
+    x = rng.randn(100_003).astype(np.float32)
+    t = dev(x)
+    out = torch.empty_like(t)
+    for off in (0, 1, 2, 3):                                # 4-byte aligned only: scalar path
+        n = x.size - off - 5
+        rc = lib.scir_b200_add_scalar_f32(ctx.handle, C.c_void_p(t.data_ptr() + 4 * off), 2.5,
+                                          C.c_void_p(out.data_ptr() + 4 * off), n)
+        assert rc == 0, L.last_error()
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy()[off:off + n], O.add_scalar_f32(x[off:off + n], 2.5))
+    rc = lib.scir_b200_add_f32(ctx.handle, C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()), x.size)
+    assert rc == 0
+    ctx.sync()
+    assert np.array_equal(t.cpu().numpy(), x + x)           # in place, y aliases a and b
+    assert lib.scir_b200_add_f32(ctx.handle, None, None, None, 0) == 0            # empty
+    assert lib.scir_b200_mul_scalar_f32(ctx.handle, None, 1.0, None, 5) != 0      # NULL with n > 0
+
+
 def test_mg_row_sharding_matches_single_device():
     ndev = gpu.device_count()
     if ndev < 2:
