@@ -194,6 +194,7 @@ SCIR_B200_API int scir_b200_mg_fir1d_batched_f32_host(scir_b200_mg *mg,
 
 /* ---- measurement helpers (bench.py): what the SAME box sustains, as roofline denominators ----- */
 SCIR_B200_API int scir_b200_microbench_ffma(scir_b200_ctx *ctx, int iters, double *tflops);      /* FP32 FFMA peak   */
+SCIR_B200_API int scir_b200_microbench_ffma2(scir_b200_ctx *ctx, int iters, int mix, double *tflops); /* packed FFMA2 (+mix) */
 SCIR_B200_API int scir_b200_microbench_copy(scir_b200_ctx *ctx, size_t bytes, int iters, double *gbps); /* HBM rd+wr */
 
 #ifdef __cplusplus

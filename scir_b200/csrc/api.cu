@@ -357,6 +357,7 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
     if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
+    if (ctx->toep_flags.ptr) cudaFree(ctx->toep_flags.ptr);
     for (int i = 0; i < 3; ++i) {
         if (ctx->stage_in[i].ptr) cudaFree(ctx->stage_in[i].ptr);
         if (ctx->stage_out[i].ptr) cudaFree(ctx->stage_out[i].ptr);
@@ -427,6 +428,10 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
     if (!value) return set_error(SCIR_B200_ERR_INVALID_ARG, "value is NULL");
     if (key && !strcmp(key, "toeplitz_launches")) {                   // read-only statistic
         *value = static_cast<int64_t>(ctx->toeplitz_launches);
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "fixup_launches")) {                   // read-only statistic
+        *value = static_cast<int64_t>(ctx->fixup_launches);
         return SCIR_B200_OK;
     }
     if (key && !strcmp(key, "poly_launches")) {                       // read-only statistic

@@ -60,9 +60,11 @@ struct scir_b200_ctx {
     int max_smem_optin = 0;
     uint64_t launches = 0;
     uint64_t toeplitz_launches = 0;        // launches served by the tcgen05 Toeplitz kernel
+    uint64_t fixup_launches = 0;           // non-finite fix-up kernels (one after every FIR launch; idle on finite data)
     uint64_t poly_launches = 0;            // launches served by the polyphase TILE kernel (tests)
     scir_b200::Options opt;
     scir_b200::DeviceBuffer scratch;       // filtfilt intermediate etc.
+    scir_b200::DeviceBuffer toep_flags;    // per-tile non-finite flags of the last Toeplitz launch
     // *_host streaming pipeline resources (lazily created)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     scir_b200::DeviceBuffer stage_in[3], stage_out[3];

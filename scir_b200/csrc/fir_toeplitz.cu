@@ -93,6 +93,7 @@ struct ToepParams {
     int hank_cores;                     // 16 * pmax + 31
     unsigned buf_bytes;                 // one buffer (multiple of 128)
     float tap_scale, tap_inv;           // power of two applied to the taps (fmt 0) and its inverse
+    int* tile_flags;                    // [total_tiles]: 1 if the tile's slab held a NaN / Inf sample (see toeplitz_fixup_kernel)
 };
 
 // ---- tcgen05 / TMEM PTX ----------------------------------------------------------------------------------
@@ -522,16 +523,19 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         };
         // block-wide max -> power-of-two scale (fmt 0); the named barrier doubles as the "everyone has
         // read the raw tile" point of the in-place conversion
-        auto slab_scale = [&](int it) -> float {
+        auto slab_scale = [&](int it, int t) -> float {
+            // One reduction per slab, both formats: a non-finite sample cannot be represented by the split (and
+            // 0 * NaN would spread it over its whole 128-sample block), so such tiles are flagged and redone
+            // exactly by toeplitz_fixup_kernel.  In FP16 mode the max also sets the block scale.
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, mx);
+            if (lane == 0) red_slots[it & 1][lw] = wm;
+            asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
+            uint32_t m = *(volatile uint32_t*)&red_slots[it & 1][lane & (kLoadWarps - 1)];
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (tl == 0) q.tile_flags[t] = (m >= 0x7f800000u) ? 1 : 0;
             if constexpr (!F16) {
-                if (inplace) asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
                 return 1.f;
             } else {
-                const uint32_t wm = __reduce_max_sync(0xffffffffu, mx);
-                if (lane == 0) red_slots[it & 1][lw] = wm;
-                asm volatile("bar.sync 1, %0;" ::"n"(kLoadThreads) : "memory");
-                uint32_t m = *(volatile uint32_t*)&red_slots[it & 1][lane & (kLoadWarps - 1)];
-                m = __reduce_max_sync(0xffffffffu, m);
                 // scale = 2^(141 - E): max|x| * scale in [2^14, 2^15); exponent field kept in [14, 253] so that
                 // both the scale and its inverse are normal numbers
                 const int e = static_cast<int>(m >> 23);
@@ -578,7 +582,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
                 if (tile_bulk(tile_ipA(ct))) gather_smem(reinterpret_cast<const float*>(smem_raw + boff));
                 else fetch(t);
                 local_max();
-                const float scale = slab_scale(it);        // barrier: every converter holds its part of the tile
+                const float scale = slab_scale(it, t);     // barrier: every converter holds its part of the tile
                 store_slab(smem0 + boff, scale);
                 fence_proxy_async_smem();                  // my generic-proxy writes -> visible to the MMA's async reads
                 mbar_arrive(BAR(SLAB_FULL, buf));
@@ -591,7 +595,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
             if (static_cast<int>(blockIdx.x) < ntiles) fetch(blockIdx.x);
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
                 local_max();
-                const float scale = slab_scale(it);
+                const float scale = slab_scale(it, t);
                 mbar_wait(BAR(BUF_EMPTY, buf), par ^ 1u);
                 store_slab(smem0 + buf0_off + static_cast<uint32_t>(buf) * q.buf_bytes, scale);
                 fence_proxy_async_smem();
@@ -696,6 +700,31 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// Tiles whose slab held a NaN / Inf sample are recomputed here the way the FP32 direct kernels (and the
+// reference loop, crates/scir-gpu/src/lib.rs:1138-1150) do it: one FMA chain per output, so the non-finite value
+// reaches exactly the outputs whose window contains it.  Launched after every Toeplitz pass; with finite
+// data it reads total_tiles flags from L2 and exits (~3 us).
+__global__ void __launch_bounds__(256) toeplitz_fixup_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
+{
+    const FirPass& p = q.p;
+    for (int t = blockIdx.x; t < q.total_tiles; t += gridDim.x) {
+        if (q.tile_flags[t] == 0) continue;
+        const int row = t / q.tiles_per_row;
+        const int ct = t - row * q.tiles_per_row;
+        const long long ip0 = (q.first_col + static_cast<long long>(ct) * TN) * TB - q.org;
+        const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
+        float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
+        for (int o = threadIdx.x; o < TB * TN; o += blockDim.x) {
+            const long long ip = ip0 + o;
+            if (ip < q.ip_lo || ip >= q.ip_hi) continue;
+            const long long i = map_index(p, ip);                      // virtual index of this output
+            float acc = 0.f;
+            for (int d = 0; d < q.k; ++d) acc = fmaf(taps.c[d], tload(p, xr, p.dir > 0 ? i - d : i + d), acc);
+            yr[i] = acc;
+        }
     }
 }
 
@@ -818,10 +847,15 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
                   "cudaFuncSetAttribute(fir_toeplitz_kernel)");
         configured[d][flavour] = plan.smem_bytes;
     }
+    SCIR_TRY(ctx_scratch(ctx, ctx->toep_flags, static_cast<size_t>(plan.q.total_tiles) * sizeof(int)));
+    plan.q.tile_flags = static_cast<int*>(ctx->toep_flags.ptr);
     const int grid = std::min(plan.q.total_tiles, ctx->sm_count);
     kern<<<grid, kToepThreads, plan.smem_bytes, ctx->stream>>>(plan.q, *tl);
     SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
-    ctx->launches++;
+    toeplitz_fixup_kernel<<<std::min(plan.q.total_tiles, ctx->sm_count * 8), 256, 0, ctx->stream>>>(plan.q, *tl);
+    SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
+    ctx->launches += 2;                                    // the contraction and its (normally idle) fix-up
+    ctx->fixup_launches++;
     ctx->toeplitz_launches++;
     return SCIR_B200_OK;
 }

@@ -31,6 +31,46 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, c
     if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // defeat DCE, never true
 }
 
+// Packed form: FFMA2 Racc.F32x2, Rx.F32 (broadcast), URtaps.F32x2, Racc.F32x2 -- two FMAs per issue slot.
+// MIX extra integer instructions per 8 FFMA2 probe how many non-FMA issue slots ride along for free.
+__device__ __forceinline__ void fma2(unsigned long long& acc, float x, float t0, float t1)
+{
+    unsigned long long xx, tt;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(tt) : "f"(t0), "f"(t1));
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(tt));
+}
+
+template <int R2, int MIX>
+__global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, const __grid_constant__ MbTaps taps)
+{
+    unsigned long long acc[R2];
+    float x[4];
+    unsigned junk = threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R2; ++r) acc[r] = 0ull;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = 1e-3f * static_cast<float>(threadIdx.x + e);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int t = 0; t < 64; t += 2) {
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                fma2(acc[r], x[(t + r) & 3], taps.c[t], taps.c[t + 1]);
+                if (MIX > 0 && (r % (8 / MIX)) == 0) junk = junk * 3u + 1u;       // one IMAD per 8/MIX FFMA2
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[r]));
+        s += lo + hi;
+    }
+    if (s == 123.456f || junk == 0x12345u) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // defeat DCE
+}
+
 __global__ void copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4)
 {
     size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -67,6 +107,46 @@ int scir_b200_microbench_ffma(scir_b200_ctx* ctx, int iters, double* tflops)
     float ms = 0.f;
     SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
     const double flops = 2.0 * blocks * 256.0 * iters * 64.0 * R;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return SCIR_B200_OK;
+}
+
+// mix = 0: pure FFMA2 stream; mix = 1, 2, 4, 8: that many extra integer instructions per 8 FFMA2
+int scir_b200_microbench_ffma2(scir_b200_ctx* ctx, int iters, int mix, double* tflops)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!tflops || iters < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
+    SCIR_TRY(ctx_bind(ctx));
+    constexpr int R2 = 10;
+    const int blocks = ctx->sm_count * 8;
+    float* d_out = nullptr;
+    SCIR_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_out), static_cast<size_t>(blocks) * 256 * 4), "cudaMalloc");
+    MbTaps taps;
+    for (int i = 0; i < 64; ++i) taps.c[i] = 1e-4f * static_cast<float>(i + 1);
+    cudaEvent_t e0, e1;
+    SCIR_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
+    SCIR_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
+    auto launch = [&]() {
+        switch (mix) {
+            case 1: ffma2_peak_kernel<R2, 1><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps); break;
+            case 2: ffma2_peak_kernel<R2, 2><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps); break;
+            case 4: ffma2_peak_kernel<R2, 4><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps); break;
+            case 8: ffma2_peak_kernel<R2, 8><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps); break;
+            default: ffma2_peak_kernel<R2, 0><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, taps); break;
+        }
+    };
+    launch();                                                                          // warm-up
+    SCIR_CUDA(cudaEventRecord(e0, ctx->stream), "cudaEventRecord");
+    launch();
+    SCIR_CUDA(cudaEventRecord(e1, ctx->stream), "cudaEventRecord");
+    SCIR_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+    ctx->launches += 2;
+    float ms = 0.f;
+    SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+    const double flops = 2.0 * blocks * 256.0 * iters * 32.0 * (2 * R2);      // 32 tap pairs x R2 FFMA2 x 2 FMAs
     *tflops = flops / (ms * 1e-3) / 1e12;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -48,6 +48,97 @@ struct PolyParams {
     int in_vec_ok, out_vec_ok;
 };
 
+// ---- packed FP32 (FFMA2) form ------------------------------------------------------------------------
+// sm_100 issues `FFMA2 Racc.F32x2, Rx.F32, URtaps.F32x2, Racc.F32x2`: two FMAs per issue slot, the sample
+// broadcast, the two taps a uniform-register pair.  Measured (scir_b200_microbench_ffma2): 74.0 TFLOP/s = 99 % of
+// the nominal FP32 peak against 67.7 for the scalar FFMA stream, and -- what matters at the ridge -- only HALF
+// the issue slots are spent on arithmetic, so loads, stores and loop control ride along for free.
+// A thread's outputs are paired (j, j+1); for every window sample s the pair's two taps (either may be a
+// structural zero) are precomputed on the host into a table laid out in exactly the order the fully
+// unrolled loop consumes it, so each FFMA2 takes its taps with one LDCU.64 at a compile-time offset.
+constexpr int kPolyMaxPairs = 768;
+
+struct PolyPairs {
+    float2 p[kPolyMaxPairs];
+};
+
+template <int UP, int DOWN, int G, int KCP, int Z>
+struct PolyGeom {
+    static constexpr int R = UP * G;
+    static constexpr int ZP = (Z > 0) ? 4 : 0;
+    static constexpr int DQMAX = ((R - 1) * DOWN) / UP;
+    static constexpr int W4 = (KCP + ZP + DQMAX + 1 + 3) / 4;
+    // index into the (single-chunk) tap array of the tap that output j of a thread applies to window sample s, or -1
+    __host__ __device__ static constexpr int tap_of(int j, int s)
+    {
+        const int tj = (j * DOWN) % UP, dq = (j * DOWN) / UP, ot = (tj < Z) ? 1 : 0;
+        const int il = dq + KCP + ZP - s - ot;
+        return (il >= 0 && il < KCP) ? (il + ot) * UP + tj : -1;
+    }
+    __host__ __device__ static constexpr int pair_count()
+    {
+        int n = 0;
+        for (int s = 0; s < 4 * W4; ++s)
+            for (int p = 0; p < R / 2; ++p)
+                if (tap_of(2 * p, s) >= 0 || tap_of(2 * p + 1, s) >= 0) ++n;
+        return n;
+    }
+    static void fill_pairs(const float* c, PolyPairs* out)     // host: same enumeration order as poly_core2
+    {
+        int n = 0;
+        for (int s = 0; s < 4 * W4; ++s)
+            for (int p = 0; p < R / 2; ++p) {
+                const int a = tap_of(2 * p, s), b = tap_of(2 * p + 1, s);
+                if (a >= 0 || b >= 0) out->p[n++] = make_float2(a >= 0 ? c[a] : 0.f, b >= 0 ? c[b] : 0.f);
+            }
+    }
+};
+
+__device__ __forceinline__ void fma2_bcast(unsigned long long& acc, float x, const float2& taps)
+{
+    unsigned long long xx;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(*reinterpret_cast<const unsigned long long*>(&taps)));
+}
+
+template <int UP, int DOWN, int G, int KCP, int Z>
+__device__ __forceinline__ void poly_core2(float (&acc)[UP * G], const float* wbase, const PolyTaps& taps, const PolyPairs& pairs)
+{
+    using Geo = PolyGeom<UP, DOWN, G, KCP, Z>;
+    constexpr int R = Geo::R;
+    static_assert(Geo::pair_count() <= kPolyMaxPairs, "pair table too small");
+    unsigned long long acc2[R / 2];
+    float tail = 0.f;                                              // odd R: the last output stays scalar
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) acc2[p] = 0ull;
+    const float4* w = reinterpret_cast<const float4*>(wbase - KCP - Geo::ZP);
+    int cnt = 0;                                                   // compile-time after unrolling
+#pragma unroll
+    for (int v4 = 0; v4 < Geo::W4; ++v4) {
+        const float4 v = w[v4];
+        const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int s = 4 * v4 + e;
+#pragma unroll
+            for (int p = 0; p < R / 2; ++p) {
+                if (Geo::tap_of(2 * p, s) >= 0 || Geo::tap_of(2 * p + 1, s) >= 0) {
+                    fma2_bcast(acc2[p], xv[e], pairs.p[cnt]);
+                    ++cnt;
+                }
+            }
+            if constexpr (R % 2 == 1) {
+                const int a = Geo::tap_of(R - 1, s);
+                if (a >= 0) tail = fmaf(taps.c[a], xv[e], tail);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * p]), "=f"(acc[2 * p + 1]) : "l"(acc2[p]));
+    if constexpr (R % 2 == 1) acc[R - 1] = tail;
+}
+
 // The FFMA core shared by the tile and the streaming kernel: R = UP*G outputs of one thread, x-major over the
 // window, taps as constant-bank operands.  wbase points at the thread's sample q0_thread.
 template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
@@ -189,7 +280,8 @@ upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant_
 // the whole game.
 template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
 __global__ void __launch_bounds__(kPolyNT, 3)
-upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps, long long batch)
+upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps, long long batch,
+                      const __grid_constant__ PolyPairs pairs, int packed)
 {
     constexpr int NT = kPolyNT;
     constexpr int R = UP * G;
@@ -267,7 +359,12 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
         }
 
         float acc[R];
-        poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, in + HALO + tid * SIN, nchunk, taps);
+        if constexpr (NCH == 1) {
+            if (packed) poly_core2<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
+            else poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, in + HALO + tid * SIN, nchunk, taps);
+        } else {
+            poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, in + HALO + tid * SIN, nchunk, taps);
+        }
 
         if (tid == 0) bulk_store_wait_read<0>();           // the previous tile's store has drained `out`
         __syncthreads();                                   // A: in[s] consumed by every warp, out free
@@ -320,7 +417,11 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
             occ_smem[d] = stream_bytes;
         }
         const long long g = std::min<long long>(grid, static_cast<long long>(ctx->sm_count) * resident[d]);
-        kern<<<static_cast<unsigned>(g), kPolyNT, stream_bytes, ctx->stream>>>(q, taps, batch);
+        thread_local PolyPairs* pairs = nullptr;
+        if (!pairs) pairs = new PolyPairs();
+        const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4) ? 1 : 0;   // upfirdn_variant=4: scalar-FFMA A/B arm
+        if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
+        kern<<<static_cast<unsigned>(g), kPolyNT, stream_bytes, ctx->stream>>>(q, taps, batch, *pairs, packed);
         SCIR_CUDA(cudaGetLastError(), "upfirdn_stream_kernel launch");
         ctx->launches++;
         ctx->poly_launches++;

@@ -139,6 +139,38 @@ def test_toeplitz_single_accumulation_chain(k, loader):
         assert np.abs(y - want).max() <= tol(taps, x), (chains, ts)
 
 
+@pytest.mark.parametrize("loader,split", [(0, 0), (1, 0), (0, 1)])
+@pytest.mark.parametrize("k", [63, 300])
+def test_toeplitz_non_finite_samples_stay_local(k, loader, split):
+    """A NaN / Inf sample must reach exactly the outputs whose window contains it (what the reference loop and
+    the FP32 kernels do), not its whole 128 x 128 tile: flagged tiles are redone by the fix-up kernel."""
+    rng = np.random.RandomState(k + loader)
+    x = (rng.rand(3, 60000).astype(np.float32) * 2 - 1)
+    taps = np.abs(rng.randn(k)).astype(np.float32) + 0.1            # positive taps: +Inf stays +Inf
+    bad = {0: [(100, np.nan)], 1: [(16384 - 5, np.inf), (40000, -np.inf)], 2: []}
+    for r, lst in bad.items():
+        for pos, v in lst:
+            x[r, pos] = v
+    ctx = toep_ctx(3, loader, split)
+    y = run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=ctx)).cpu().numpy()
+    direct = gpu.Context(0)
+    direct.set_option("long_tap_path", 1)
+    yd = run(direct, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=direct)).cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        ref = O.fir1d_batched_f32(x, taps)                          # the reference loop itself (lib.rs:1134-1152)
+    for got in (y, yd):                                             # tensor path and FP32 direct path
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        assert np.array_equal(np.isposinf(got), np.isposinf(ref)) and np.array_equal(np.isneginf(got), np.isneginf(ref))
+    for r, lst in bad.items():
+        mask = np.ones(x.shape[1], bool)
+        for pos, _ in lst:
+            mask[pos:pos + k] = False                                # kernel order: sample i feeds outputs i .. i+k-1
+        assert np.isfinite(y[r][mask]).all()
+        xs = np.where(np.isfinite(x[r]), x[r], 0).astype(np.float32)[None, :]
+        want = O.fir1d_batched_f32_acc64(xs, taps)[0]
+        assert np.abs(y[r][mask] - want[mask]).max() <= tol(taps, xs)
+
+
 def test_toeplitz_many_tiles_and_views():
     """More tiles than SMs (persistent CTAs wrap both pipelines), unaligned rows (scalar loader path)."""
     rng = np.random.RandomState(3)
