@@ -44,9 +44,9 @@ struct FirTileParams {
     long long base0;      // virtual index of the first output of tile 0 ((base0 + in_off) % 4 == 0)
     long long ntiles;     // tiles per row
     int nchunk;           // tap chunks (halo = nchunk * KC)
+    int k;                // true tap count (non-finite redo)
     int in_vec_ok;        // input rows are 16-B aligned => interior tiles may use the bulk copy
     int out_vec_ok;       // same for the output side
-    int* tile_flags;      // [batch * ntiles]: 1 if a tile produced a non-finite output (see fir_fixup_kernel)
 };
 
 // ---- virtual input sequence (edge tiles only) ------------------------------------------------------
@@ -106,16 +106,29 @@ __device__ __forceinline__ void fir_core(float (&acc)[R], const float* wbase, in
 }
 
 // Non-finite data: the tap array is zero-padded to whole chunks, and 0 * Inf = NaN would leak a stray Inf / NaN
-// into up to KC-1 outputs whose true window does not contain it.  Tiles that produced any non-finite output
-// are flagged (one extra compare per output, folded into a barrier that is there anyway) and recomputed by
-// fir_fixup_kernel with exactly k taps, the way the reference loop does (lib.rs:1138-1150).
+// into up to KC-1 outputs whose true window does not contain it.  A thread whose outputs came out non-finite
+// (one add per output to find out) redoes them from the staged window with exactly k taps, the way the
+// reference loop does (lib.rs:1138-1150); with finite data the branch is never taken.
 template <int R>
-__device__ __forceinline__ int any_nonfinite(const float (&acc)[R])
+__device__ __forceinline__ bool any_nonfinite(const float (&acc)[R])
 {
-    int bad = 0;
+    // Inf and NaN survive a sum (Inf - Inf = NaN); a finite sum that overflows only costs a harmless redo
+    float s = acc[0];
 #pragma unroll
-    for (int r = 0; r < R; ++r) bad |= ((__float_as_uint(acc[r]) & 0x7f800000u) == 0x7f800000u);
-    return bad;
+    for (int r = 1; r < R; ++r) s += acc[r];
+    return (__float_as_uint(s) & 0x7f800000u) == 0x7f800000u;
+}
+
+// w0: the thread's first output position in the staged window (smem index DP + tid*R causal, tid*R anticausal)
+template <int R, int DIR, int MAXK>
+__device__ __forceinline__ void exact_redo(float (&acc)[R], const float* w0, int k, const TapsParam<MAXK>& taps)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float a = 0.f;
+        for (int d = 0; d < k; ++d) a = fmaf(taps.c[d], (DIR > 0) ? w0[r - d] : w0[r + d], a);
+        acc[r] = a;
+    }
 }
 
 // ---- one tile per CTA (variant 3; the round-1 first cut, kept for A/B profiling) ---------------------
@@ -164,8 +177,8 @@ fir_tile_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__
     fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R), q.nchunk, taps);
 
     // ---- results back through shared memory, then one bulk store --------------------------------------
-    const int bad = __syncthreads_or(any_nonfinite<R>(acc));   // every warp is done reading the tile
-    if (tid == 0) q.tile_flags[bid] = bad;
+    if (any_nonfinite<R>(acc)) exact_redo<R, DIR, MAXK>(acc, (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R), q.k, taps);
+    __syncthreads();                                       // every warp is done reading the tile
     float4* so = reinterpret_cast<float4*>(smem + tid * R);
 #pragma unroll
     for (int r = 0; r < R; r += 4) so[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
@@ -282,11 +295,9 @@ fir_stream_kernel(const __grid_constant__ FirTileParams q, const __grid_constant
         fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.nchunk, taps);
 
         if (tid == 0) bulk_store_wait_read<0>();           // the previous tile's store has drained `out`
-        const int bad = __syncthreads_or(any_nonfinite<R>(acc));   // A: in[s] consumed by every warp, out free
-        if (tid == 0) {
-            q.tile_flags[cur.row * q.ntiles + cur.tile] = bad;
-            prefetch(nxt, s);                              // refill in[s] two tiles ahead
-        }
+        if (any_nonfinite<R>(acc)) exact_redo<R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.k, taps);
+        __syncthreads();                                   // A: in[s] consumed by every warp, out free
+        if (tid == 0) prefetch(nxt, s);                    // refill in[s] two tiles ahead
 
         float4* so = reinterpret_cast<float4*>(out_s + tid * R);
 #pragma unroll
@@ -306,28 +317,6 @@ fir_stream_kernel(const __grid_constant__ FirTileParams q, const __grid_constant
         }
     }
     if (tid == 0) bulk_store_wait_read<0>();               // smem must outlive the last store's read
-}
-
-template <int MAXK>
-__global__ void __launch_bounds__(256) fir_fixup_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__ TapsParam<MAXK> taps,
-                                                        int k, int tile_len)
-{
-    const FirPass& p = q.p;
-    const long long total = q.ntiles * p.batch;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        if (q.tile_flags[t] == 0) continue;
-        const long long row = t / q.ntiles, tile = t - row * q.ntiles;
-        const long long i0 = q.base0 + tile * tile_len;
-        const float* __restrict__ xr = p.x + row * p.ld_x;
-        float* __restrict__ yr = p.y + row * p.ld_y;
-        for (int o = threadIdx.x; o < tile_len; o += blockDim.x) {
-            const long long i = i0 + o;
-            if (i < p.out_begin || i >= p.out_end) continue;
-            float acc = 0.f;
-            for (int d = 0; d < k; ++d) acc = fmaf(taps.c[d], vload(p, xr, p.dir > 0 ? i - d : i + d), acc);
-            yr[i + p.out_off] = acc;
-        }
-    }
 }
 
 // ---- the warp-streaming kernel (default for K <= 256) ---------------------------------------------------
@@ -537,16 +526,11 @@ int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int6
         }
         grid = std::min<long long>(total, static_cast<long long>(ctx->sm_count) * resident[d][f]);
     }
-    SCIR_TRY(ctx_scratch(ctx, ctx->toep_flags, static_cast<size_t>(total) * sizeof(int)));
     FirTileParams qq = q;
-    qq.tile_flags = static_cast<int*>(ctx->toep_flags.ptr);
+    qq.k = static_cast<int>(k);
     kern<<<static_cast<unsigned>(grid), kNT, smem_bytes, ctx->stream>>>(qq, *tl);
     SCIR_CUDA(cudaGetLastError(), "fir kernel launch");
-    fir_fixup_kernel<MAXK><<<static_cast<unsigned>(std::min<long long>(total, static_cast<long long>(ctx->sm_count) * 8)), 256, 0,
-                             ctx->stream>>>(qq, *tl, static_cast<int>(k), kTile);
-    SCIR_CUDA(cudaGetLastError(), "fir_fixup_kernel launch");
-    ctx->launches += 2;                                    // the FIR kernel and its (normally idle) non-finite fix-up
-    ctx->fixup_launches++;
+    ctx->launches++;
     return SCIR_B200_OK;
 }
 

@@ -710,21 +710,32 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
 __global__ void __launch_bounds__(256) toeplitz_fixup_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
 {
     const FirPass& p = q.p;
-    for (int t = blockIdx.x; t < q.total_tiles; t += gridDim.x) {
-        if (q.tile_flags[t] == 0) continue;
-        const int row = t / q.tiles_per_row;
-        const int ct = t - row * q.tiles_per_row;
-        const long long ip0 = (q.first_col + static_cast<long long>(ct) * TN) * TB - q.org;
-        const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
-        float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
-        for (int o = threadIdx.x; o < TB * TN; o += blockDim.x) {
-            const long long ip = ip0 + o;
-            if (ip < q.ip_lo || ip >= q.ip_hi) continue;
-            const long long i = map_index(p, ip);                      // virtual index of this output
-            float acc = 0.f;
-            for (int d = 0; d < q.k; ++d) acc = fmaf(taps.c[d], tload(p, xr, p.dir > 0 ? i - d : i + d), acc);
-            yr[i] = acc;
+    // 256 flags per CTA trip, one per thread (coalesced); the common case is one load and one barrier
+    for (int base = blockIdx.x * 256; base < q.total_tiles; base += gridDim.x * 256) {
+        const int mine = base + threadIdx.x;
+        const int flag = (mine < q.total_tiles) ? q.tile_flags[mine] : 0;
+        if (!__syncthreads_or(flag)) continue;
+        __shared__ int hit[256];
+        hit[threadIdx.x] = flag;
+        __syncthreads();
+        for (int j = 0; j < 256; ++j) {
+            if (!hit[j]) continue;
+            const int t = base + j;
+            const int row = t / q.tiles_per_row;
+            const int ct = t - row * q.tiles_per_row;
+            const long long ip0 = (q.first_col + static_cast<long long>(ct) * TN) * TB - q.org;
+            const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
+            float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
+            for (int o = threadIdx.x; o < TB * TN; o += blockDim.x) {
+                const long long ip = ip0 + o;
+                if (ip < q.ip_lo || ip >= q.ip_hi) continue;
+                const long long i = map_index(p, ip);                  // virtual index of this output
+                float acc = 0.f;
+                for (int d = 0; d < q.k; ++d) acc = fmaf(taps.c[d], tload(p, xr, p.dir > 0 ? i - d : i + d), acc);
+                yr[i] = acc;
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -852,7 +863,7 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
     const int grid = std::min(plan.q.total_tiles, ctx->sm_count);
     kern<<<grid, kToepThreads, plan.smem_bytes, ctx->stream>>>(plan.q, *tl);
     SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
-    toeplitz_fixup_kernel<<<std::min(plan.q.total_tiles, ctx->sm_count * 8), 256, 0, ctx->stream>>>(plan.q, *tl);
+    toeplitz_fixup_kernel<<<std::min((plan.q.total_tiles + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(plan.q, *tl);
     SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
     ctx->launches += 2;                                    // the contraction and its (normally idle) fix-up
     ctx->fixup_launches++;
