@@ -121,6 +121,18 @@ SCIR_B200_API int scir_b200_lfilter_fir_f32(scir_b200_ctx *ctx,
 /* _output_len (scipy/signal/_upfirdn_apply.pyx:59-67), pure int64. */
 SCIR_B200_API int64_t scir_b200_upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);
 
+/* Signal-extension modes of upfirdn / resample_poly: values = SciPy's MODE enum (_upfirdn_apply.pyx:77-86),
+ * names = its mode strings (pyx:89-105: 'constant', 'symmetric', 'edge', 'smooth', 'wrap', 'reflect',
+ * 'antisymmetric', 'antireflect', 'line').  Modes that reflect need n_in >= 2 where SciPy divides by n_in-1. */
+enum {
+    SCIR_B200_EXT_CONSTANT = 0, SCIR_B200_EXT_SYMMETRIC = 1, SCIR_B200_EXT_EDGE = 2, SCIR_B200_EXT_SMOOTH = 3,
+    SCIR_B200_EXT_PERIODIC = 4, SCIR_B200_EXT_REFLECT = 5, SCIR_B200_EXT_ANTISYMMETRIC = 6,
+    SCIR_B200_EXT_ANTIREFLECT = 7, SCIR_B200_EXT_LINE = 8
+};
+/* resample_poly padtypes beyond the extension modes (_signaltools.py:3921-3957): a per-row statistic is removed
+ * before and restored after a zero-padded upfirdn.  MEDIAN is not implemented on the device yet (UNSUPPORTED). */
+enum { SCIR_B200_PAD_STAT_MEAN = 16, SCIR_B200_PAD_STAT_MEDIAN = 17, SCIR_B200_PAD_STAT_MINIMUM = 18, SCIR_B200_PAD_STAT_MAXIMUM = 19 };
+
 /* upfirdn(h, x, up, down), mode='constant' (pyx:421-481): writes outputs m in
  * [m_begin, m_begin+m_count) of each row to d_y[b, 0..m_count); the full result is
  * m_begin=0, m_count=scir_b200_upfirdn_out_len(len_h, n_in, up, down). */
@@ -128,6 +140,12 @@ SCIR_B200_API int scir_b200_upfirdn_f32(scir_b200_ctx *ctx,
                           const float *h, int64_t len_h, int64_t up, int64_t down,
                           const float *d_x, int64_t ld_x, int64_t batch, int64_t n_in,
                           float *d_y, int64_t ld_y, int64_t m_begin, int64_t m_count);
+
+/* Same with a signal-extension mode (pyx:110-231): samples outside [0, n_in) take the mode's value instead of 0. */
+SCIR_B200_API int scir_b200_upfirdn_mode_f32(scir_b200_ctx *ctx,
+                               const float *h, int64_t len_h, int64_t up, int64_t down, int mode, float cval,
+                               const float *d_x, int64_t ld_x, int64_t batch, int64_t n_in,
+                               float *d_y, int64_t ld_y, int64_t m_begin, int64_t m_count);
 
 /* Integer plan of resample_poly (scipy/signal/_signaltools.py:3882-3918); bit-exact contract. */
 typedef struct {
@@ -149,6 +167,12 @@ SCIR_B200_API int scir_b200_resample_poly_f32(scir_b200_ctx *ctx,
                                 const float *window, int64_t len_h, int64_t up, int64_t down,
                                 const float *d_x, int64_t ld_x, int64_t batch, int64_t n_in,
                                 float *d_y, int64_t ld_y);
+/* resample_poly(..., padtype, cval): padtype = SCIR_B200_EXT_* or SCIR_B200_PAD_STAT_*; cval for EXT_CONSTANT. */
+SCIR_B200_API int scir_b200_resample_poly_pad_f32(scir_b200_ctx *ctx,
+                                    const float *window, int64_t len_h, int64_t up, int64_t down,
+                                    int padtype, float cval,
+                                    const float *d_x, int64_t ld_x, int64_t batch, int64_t n_in,
+                                    float *d_y, int64_t ld_y);
 SCIR_B200_API int scir_b200_resample_poly_f32_host(scir_b200_ctx *ctx,
                                      const float *window, int64_t len_h, int64_t up, int64_t down,
                                      const float *h_x, int64_t ld_x, int64_t batch, int64_t n_in,

@@ -345,6 +345,139 @@ ORACLE_API void oracle_upfirdn_f64(const double *h, int64_t len_h, const double 
 }
 
 /* ------------------------------------------------------------------------- */
+/* SciPy upfirdn signal-extension modes (_upfirdn_apply.pyx:76-231, :421-481).  */
+/* ------------------------------------------------------------------------- */
+/* MODE enum of pyx:77-86 */
+enum { OMODE_CONSTANT = 0, OMODE_SYMMETRIC = 1, OMODE_CONSTANT_EDGE = 2, OMODE_SMOOTH = 3, OMODE_PERIODIC = 4,
+       OMODE_REFLECT = 5, OMODE_ANTISYMMETRIC = 6, OMODE_ANTIREFLECT = 7, OMODE_LINE = 8 };
+
+/* C's % truncates like Cython's with cdivision(True); every left operand below is >= 0. */
+#define DEFINE_EXTEND(SUF, T)                                                                        \
+static T extend_left_##SUF(const T *x, int64_t idx, int64_t len_x, int mode, T cval)   /* pyx:110-170 */ \
+{                                                                                                    \
+    T le, lin_slope;                                                                                 \
+    switch (mode) {                                                                                  \
+    case OMODE_SYMMETRIC:                                                                            \
+        if ((-idx) < len_x) return x[-idx - 1];                                                      \
+        idx = (-idx - 1) % (2 * len_x);                                                              \
+        return (idx < len_x) ? x[idx] : x[len_x - 1 - (idx - len_x)];                                \
+    case OMODE_REFLECT:                                                                              \
+        if ((-idx) < (len_x - 1)) return x[-idx];                                                    \
+        idx = (-idx - 1) % (2 * (len_x - 1));                                                        \
+        return (idx < (len_x - 1)) ? x[idx + 1] : x[len_x - 2 - (idx - (len_x - 1))];                \
+    case OMODE_PERIODIC:                                                                             \
+        idx = (-idx - 1) % len_x;                                                                    \
+        return x[len_x - idx - 1];                                                                   \
+    case OMODE_SMOOTH:                                                                               \
+        return x[0] + (T)idx * (x[1] - x[0]);                                                        \
+    case OMODE_LINE:                                                                                 \
+        lin_slope = (x[len_x - 1] - x[0]) / (T)(len_x - 1);                                          \
+        return x[0] + (T)idx * lin_slope;                                                            \
+    case OMODE_ANTISYMMETRIC:                                                                        \
+        if ((-idx) < len_x) return -x[-idx - 1];                                                     \
+        idx = (-idx - 1) % (2 * len_x);                                                              \
+        return (idx < len_x) ? -x[idx] : x[len_x - 1 - (idx - len_x)];                               \
+    case OMODE_ANTIREFLECT:                                                                          \
+        if ((-idx) < len_x) return x[0] - (x[-idx] - x[0]);                                          \
+        le = x[0] + (x[0] - x[len_x - 1]) * (T)((-(idx) - 1) / (len_x - 1));                         \
+        idx = (-idx - 1) % (2 * (len_x - 1));                                                        \
+        return (idx < (len_x - 1)) ? le - (x[idx + 1] - x[0])                                        \
+                                   : le - (x[len_x - 1] - x[len_x - 2 - (idx - (len_x - 1))]);       \
+    case OMODE_CONSTANT_EDGE: return x[0];                                                           \
+    case OMODE_CONSTANT: return cval;                                                                \
+    default: return (T)-1;                                                                           \
+    }                                                                                                \
+}                                                                                                    \
+static T extend_right_##SUF(const T *x, int64_t idx, int64_t len_x, int mode, T cval)  /* pyx:176-231 */ \
+{                                                                                                    \
+    T re, lin_slope;                                                                                 \
+    switch (mode) {                                                                                  \
+    case OMODE_SYMMETRIC:                                                                            \
+        if (idx < (2 * len_x)) return x[len_x - 1 - (idx - len_x)];                                  \
+        idx = idx % (2 * len_x);                                                                     \
+        return (idx < len_x) ? x[idx] : x[len_x - 1 - (idx - len_x)];                                \
+    case OMODE_REFLECT:                                                                              \
+        if (idx < (2 * len_x - 1)) return x[len_x - 2 - (idx - len_x)];                              \
+        idx = idx % (2 * (len_x - 1));                                                               \
+        return (idx < (len_x - 1)) ? x[idx] : x[len_x - 1 - (idx - (len_x - 1))];                    \
+    case OMODE_PERIODIC: return x[idx % len_x];                                                      \
+    case OMODE_SMOOTH:                                                                               \
+        return x[len_x - 1] + (T)(idx - len_x + 1) * (x[len_x - 1] - x[len_x - 2]);                  \
+    case OMODE_LINE:                                                                                 \
+        lin_slope = (x[len_x - 1] - x[0]) / (T)(len_x - 1);                                          \
+        return x[len_x - 1] + (T)(idx - len_x + 1) * lin_slope;                                      \
+    case OMODE_CONSTANT_EDGE: return x[len_x - 1];                                                   \
+    case OMODE_ANTISYMMETRIC:                                                                        \
+        if (idx < (2 * len_x)) return -x[len_x - 1 - (idx - len_x)];                                 \
+        idx = idx % (2 * len_x);                                                                     \
+        return (idx < len_x) ? x[idx] : -x[len_x - 1 - (idx - len_x)];                               \
+    case OMODE_ANTIREFLECT:                                                                          \
+        if (idx < (2 * len_x - 1)) return x[len_x - 1] - (x[len_x - 2 - (idx - len_x)] - x[len_x - 1]); \
+        re = x[len_x - 1] + (x[len_x - 1] - x[0]) * (T)(idx / (len_x - 1) - 1);                      \
+        idx = idx % (2 * (len_x - 1));                                                               \
+        return (idx < (len_x - 1)) ? re + (x[idx] - x[0])                                            \
+                                   : re + (x[len_x - 1] - x[len_x - 1 - (idx - (len_x - 1))]);       \
+    case OMODE_CONSTANT: return cval;                                                                \
+    default: return (T)-1;                                                                           \
+    }                                                                                                \
+}                                                                                                    \
+/* _apply_impl (pyx:421-481) with a signal-extension mode: same state machine as above, samples      \
+ * outside [0, len_x) come from extend_left / extend_right instead of being skipped. */              \
+static void upfirdn_mode_row_##SUF(const T *h, int64_t len_h, const T *x, int64_t len_x, int64_t up, \
+                                   int64_t down, int mode, T cval, double *out, int64_t len_out)     \
+{                                                                                                    \
+    const int64_t hpp = (len_h + up - 1) / up;                                                       \
+    T *htf = (T *)calloc((size_t)(hpp * up), sizeof(T));                                             \
+    for (int64_t p = 0; p < up; ++p)                                                                 \
+        for (int64_t j = 0; j < hpp; ++j) {                                                          \
+            int64_t src = p + (hpp - 1 - j) * up;                                                    \
+            htf[p * hpp + j] = (src < len_h) ? h[src] : (T)0;                                        \
+        }                                                                                            \
+    const int64_t padded_len = len_x + hpp - 1;                                                      \
+    int64_t x_idx = 0, t = 0, y_idx = 0;                                                             \
+    while (x_idx < padded_len && y_idx < len_out) {                                                  \
+        int64_t h_idx = t * hpp;                                                                     \
+        double acc = 0.0;                                                                            \
+        for (int64_t xc = x_idx - hpp + 1; xc <= x_idx; ++xc, ++h_idx) {                             \
+            T xv;                                                                                    \
+            if (xc < 0) xv = extend_left_##SUF(x, xc, len_x, mode, cval);                            \
+            else if (xc >= len_x) xv = extend_right_##SUF(x, xc, len_x, mode, cval);                 \
+            else xv = x[xc];                                                                         \
+            acc += (double)xv * (double)htf[h_idx];                                                  \
+        }                                                                                            \
+        out[y_idx++] = acc;                                                                          \
+        t += down;                                                                                   \
+        x_idx += t / up;                                                                             \
+        t %= up;                                                                                     \
+    }                                                                                                \
+    for (; y_idx < len_out; ++y_idx) out[y_idx] = 0.0;                                               \
+    free(htf);                                                                                       \
+}
+
+DEFINE_EXTEND(f32, float)
+DEFINE_EXTEND(f64, double)
+
+/* f32 data (extension values formed in f32, as SciPy does for f32 input), products and sums in f64 */
+ORACLE_API void oracle_upfirdn_mode_f32_acc64(const float *h, int64_t len_h, const float *x, int64_t batch,
+                                              int64_t len_x, int64_t up, int64_t down, int mode, double cval,
+                                              double *y)
+{
+    const int64_t lo = oracle_upfirdn_out_len(len_h, len_x, up, down);
+    for (int64_t r = 0; r < batch; ++r)
+        upfirdn_mode_row_f32(h, len_h, x + r * len_x, len_x, up, down, mode, (float)cval, y + r * lo, lo);
+}
+
+/* all-f64 twin: pins the restatement against SciPy's own f64 outputs to rounding */
+ORACLE_API void oracle_upfirdn_mode_f64(const double *h, int64_t len_h, const double *x, int64_t batch,
+                                        int64_t len_x, int64_t up, int64_t down, int mode, double cval,
+                                        double *y)
+{
+    const int64_t lo = oracle_upfirdn_out_len(len_h, len_x, up, down);
+    for (int64_t r = 0; r < batch; ++r)
+        upfirdn_mode_row_f64(h, len_h, x + r * len_x, len_x, up, down, mode, cval, y + r * lo, lo);
+}
+
+/* ------------------------------------------------------------------------- */
 /* SciPy resample_poly with an array `window` (_signaltools.py:3865-3957).    */
 /* The plan is pure int64 arithmetic and must be bit-exact.                   */
 /* ------------------------------------------------------------------------- */

@@ -14,6 +14,9 @@ ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_OOM, ERR_LAUNCH, ERR_SHAPE, ERR_UNSUPPORTED 
 MAX_TAPS = 7936
 TAPS_SCIR, TAPS_LFILTER = 0, 1
 PAD_ZERO_STATE, PAD_ODD, PAD_EVEN, PAD_CONSTANT, PAD_SCIPY_NONE = 0, 1, 2, 3, 4
+(EXT_CONSTANT, EXT_SYMMETRIC, EXT_EDGE, EXT_SMOOTH, EXT_PERIODIC, EXT_REFLECT, EXT_ANTISYMMETRIC, EXT_ANTIREFLECT,
+ EXT_LINE) = range(9)                                       # SciPy's MODE enum, _upfirdn_apply.pyx:77-86
+PAD_STAT_MEAN, PAD_STAT_MEDIAN, PAD_STAT_MINIMUM, PAD_STAT_MAXIMUM = 16, 17, 18, 19
 
 i64, vp, fp = C.c_int64, C.c_void_p, C.c_void_p   # float* passed as raw addresses
 
@@ -53,6 +56,8 @@ SIGNATURES = {
     "scir_b200_lfilter_fir_f32": (C.c_int, [vp, fp, i64, C.c_float, fp, i64, fp, fp, fp, i64, i64, i64]),
     "scir_b200_upfirdn_out_len": (i64, [i64, i64, i64, i64]),
     "scir_b200_upfirdn_f32": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64, i64, i64]),
+    "scir_b200_upfirdn_mode_f32": (C.c_int, [vp, fp, i64, i64, i64, C.c_int, C.c_float, fp, i64, i64, i64, fp, i64, i64, i64]),
+    "scir_b200_resample_poly_pad_f32": (C.c_int, [vp, fp, i64, i64, i64, C.c_int, C.c_float, fp, i64, i64, i64, fp, i64]),
     "scir_b200_resample_poly_plan": (C.c_int, [i64, i64, i64, i64, C.POINTER(ResamplePlan)]),
     "scir_b200_resample_poly_f32": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64]),
     "scir_b200_resample_poly_f32_host": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64]),

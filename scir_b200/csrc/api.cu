@@ -190,7 +190,7 @@ static int resample_plan(int64_t n_in, int64_t len_h, int64_t up, int64_t down, 
 
 static int resample_device(scir_b200_ctx* ctx, const float* window, int64_t len_h, int64_t up, int64_t down,
                            const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
-                           int64_t ld_y)
+                           int64_t ld_y, int ext_mode = 0, float cval = 0.f)
 {
     scir_b200_resample_plan pl;
     resample_plan(n_in, len_h, up, down, &pl);
@@ -206,7 +206,7 @@ static int resample_device(scir_b200_ctx* ctx, const float* window, int64_t len_
     std::vector<float> h(static_cast<size_t>(pl.len_h_padded), 0.f);
     for (int64_t i = 0; i < len_h; ++i) h[static_cast<size_t>(pl.n_pre_pad + i)] = window[i] * static_cast<float>(pl.up);
     return launch_upfirdn(ctx, h.data(), pl.len_h_padded, pl.up, pl.down, d_x, ld_x, batch, n_in, d_y, ld_y,
-                          pl.n_pre_remove, pl.n_out);
+                          pl.n_pre_remove, pl.n_out, ext_mode, cval);
 }
 
 // ---- *_host streaming: rows flow through a 3-slot ring, H2D / kernels / D2H on three streams ---------
@@ -358,6 +358,7 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
     if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
     if (ctx->toep_flags.ptr) cudaFree(ctx->toep_flags.ptr);
+    if (ctx->row_bg.ptr) cudaFree(ctx->row_bg.ptr);
     for (int i = 0; i < 3; ++i) {
         if (ctx->stage_in[i].ptr) cudaFree(ctx->stage_in[i].ptr);
         if (ctx->stage_out[i].ptr) cudaFree(ctx->stage_out[i].ptr);
@@ -605,6 +606,63 @@ int scir_b200_resample_poly_f32(scir_b200_ctx* ctx, const float* window, int64_t
     const int64_t n_out = (pl.up == 1 && pl.down == 1) ? n_in : pl.n_out;
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n_out, "y"));
     return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y);
+}
+
+int scir_b200_upfirdn_mode_f32(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down, int mode,
+                               float cval, const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
+                               int64_t ld_y, int64_t m_begin, int64_t m_count)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (!h || len_h < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "h must hold at least one tap");
+    if (up < 1 || down < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "up and down must be >= 1");   // _upfirdn.py:98
+    if (n_in < 1 && batch > 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "upfirdn needs n_in >= 1");
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n_in, "x"));
+    if (m_begin < 0 || m_count < 0 || (batch > 0 && m_begin + m_count > upfirdn_out_len(len_h, n_in, up, down)))
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "output window [%lld, %lld) outside the upfirdn result",
+                         (long long)m_begin, (long long)(m_begin + m_count));
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, m_count, "y"));
+    if (batch == 0 || m_count == 0) return SCIR_B200_OK;
+    return launch_upfirdn(ctx, h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin, m_count, mode, cval);
+}
+
+int scir_b200_resample_poly_pad_f32(scir_b200_ctx* ctx, const float* window, int64_t len_h, int64_t up, int64_t down,
+                                    int padtype, float cval, const float* d_x, int64_t ld_x, int64_t batch,
+                                    int64_t n_in, float* d_y, int64_t ld_y)
+{
+    SCIR_TRY(check_ctx(ctx));
+    scir_b200_resample_plan pl;
+    if (!window) return set_error(SCIR_B200_ERR_INVALID_ARG, "window is NULL");
+    SCIR_TRY(scir_b200_resample_poly_plan(n_in, len_h, up, down, &pl));
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n_in, "x"));
+    const bool copy = (pl.up == 1 && pl.down == 1);
+    const int64_t n_out = copy ? n_in : pl.n_out;
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, n_out, "y"));
+    if (padtype >= SCIR_B200_EXT_CONSTANT && padtype <= SCIR_B200_EXT_LINE)
+        return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, padtype, cval);
+    if (padtype == SCIR_B200_PAD_STAT_MEDIAN)
+        return set_error(SCIR_B200_ERR_UNSUPPORTED, "resample_poly padtype='median' has no device implementation yet");
+    if (padtype != SCIR_B200_PAD_STAT_MEAN && padtype != SCIR_B200_PAD_STAT_MINIMUM && padtype != SCIR_B200_PAD_STAT_MAXIMUM)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown padtype %d", padtype);
+    if (batch == 0 || n_in == 0 || copy)          // SciPy returns x.copy() before looking at padtype (:3885-3886)
+        return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y);
+    // background statistic per row, x - bg into scratch, zero-padded upfirdn, + bg (:3927-3957)
+    const int stat = (padtype == SCIR_B200_PAD_STAT_MEAN) ? 0 : (padtype == SCIR_B200_PAD_STAT_MINIMUM ? 1 : 2);
+    const int64_t ldc = (n_in + 3) / 4 * 4;
+    SCIR_TRY(ctx_scratch(ctx, ctx->row_bg, static_cast<size_t>(batch) * sizeof(float)));
+    SCIR_TRY(ctx_scratch(ctx, ctx->scratch, static_cast<size_t>(batch) * ldc * sizeof(float)));
+    float* bg = static_cast<float*>(ctx->row_bg.ptr);
+    float* xc = static_cast<float*>(ctx->scratch.ptr);
+    SCIR_TRY(launch_row_stat(ctx, stat, d_x, ld_x, batch, n_in, bg));
+    for (int64_t r0 = 0; r0 < batch; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, batch - r0);
+        SCIR_TRY(launch_row_offset(ctx, d_x + r0 * ld_x, ld_x, bg + r0, -1.f, xc + r0 * ldc, ldc, nr, n_in));
+    }
+    SCIR_TRY(resample_device(ctx, window, len_h, up, down, xc, ldc, batch, n_in, d_y, ld_y));
+    for (int64_t r0 = 0; r0 < batch; r0 += 65535) {
+        const int64_t nr = std::min<int64_t>(65535, batch - r0);
+        SCIR_TRY(launch_row_offset(ctx, d_y + r0 * ld_y, ld_y, bg + r0, +1.f, d_y + r0 * ld_y, ld_y, nr, n_out));
+    }
+    return SCIR_B200_OK;
 }
 
 int scir_b200_resample_poly_f32_host(scir_b200_ctx* ctx, const float* window, int64_t len_h, int64_t up,

@@ -65,6 +65,7 @@ struct scir_b200_ctx {
     scir_b200::Options opt;
     scir_b200::DeviceBuffer scratch;       // filtfilt intermediate etc.
     scir_b200::DeviceBuffer toep_flags;    // per-tile non-finite flags of the last Toeplitz launch
+    scir_b200::DeviceBuffer row_bg;        // resample_poly padtype statistics: one float per row
     // *_host streaming pipeline resources (lazily created)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     scir_b200::DeviceBuffer stage_in[3], stage_out[3];
@@ -115,9 +116,10 @@ int launch_compute_zf(scir_b200_ctx* ctx, const float* b, int64_t k, const float
                       const float* d_zi, float* d_zf, int64_t batch, int64_t n);
 
 // ---- polyphase upfirdn ------------------------------------------------------------------------
+// ext_mode: SCIR_B200_EXT_* (samples outside [0, n_in)), cval for EXT_CONSTANT
 int launch_upfirdn(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
                    const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
-                   int64_t ld_y, int64_t m_begin, int64_t m_count);
+                   int64_t ld_y, int64_t m_begin, int64_t m_count, int ext_mode = 0, float cval = 0.f);
 
 // ---- long-tap tensor-core path (tcgen05 block-Toeplitz) -----------------------------------------
 bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles = nullptr);
@@ -127,6 +129,10 @@ int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down)
 
 // ---- DeviceArray elementwise ops (elementwise.cu): op 0 add-scalar, 1 mul-scalar, 2 add ------------------
 int launch_elementwise(scir_b200_ctx* ctx, int op, const float* d_a, const float* d_b, float alpha, float* d_y, int64_t n);
+// per-row mean (0) / minimum (1) / maximum (2), and y = x + sign * bg[row]
+int launch_row_stat(scir_b200_ctx* ctx, int stat, const float* d_x, int64_t ld_x, int64_t batch, int64_t n, float* d_out);
+int launch_row_offset(scir_b200_ctx* ctx, const float* d_x, int64_t ld_x, const float* d_bg, float sign, float* d_y,
+                      int64_t ld_y, int64_t batch, int64_t n);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

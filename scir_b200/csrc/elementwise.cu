@@ -89,4 +89,70 @@ int launch_elementwise(scir_b200_ctx* ctx, int op, const float* d_a, const float
     return SCIR_B200_OK;
 }
 
+// ---- per-row statistics and per-row offsets: resample_poly's padtype = mean / minimum / maximum --------------
+// (scipy/signal/_signaltools.py:3921-3957: background = stat(x, axis), x - background goes through a zero-padded
+// upfirdn, background is added back).  One CTA per row, f32 pairwise-ish tree like numpy's f32 mean.
+enum { STAT_MEAN = 0, STAT_MIN = 1, STAT_MAX = 2 };
+
+template <int STAT>
+__global__ void __launch_bounds__(512) row_stat_kernel(const float* __restrict__ x, long long ld_x, long long n, float* __restrict__ out)
+{
+    const float* xr = x + static_cast<long long>(blockIdx.x) * ld_x;
+    float v = (STAT == STAT_MEAN) ? 0.f : xr[0];
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float t = xr[i];
+        v = (STAT == STAT_MEAN) ? (v + t) : (STAT == STAT_MIN ? fminf(v, t) : fmaxf(v, t));
+    }
+    __shared__ float sh[512];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 256; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const float a = sh[threadIdx.x], b = sh[threadIdx.x + s];
+            sh[threadIdx.x] = (STAT == STAT_MEAN) ? (a + b) : (STAT == STAT_MIN ? fminf(a, b) : fmaxf(a, b));
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = (STAT == STAT_MEAN) ? sh[0] / static_cast<float>(n) : sh[0];
+}
+
+// y[row, i] = x[row, i] + sign * bg[row]
+__global__ void __launch_bounds__(256) row_offset_kernel(const float* x, long long ld_x, const float* __restrict__ bg, float sign,
+                                                         float* y, long long ld_y, long long n)       // y may alias x
+{
+    const long long row = blockIdx.y;
+    const float b = sign * bg[row];
+    const float* xr = x + row * ld_x;
+    float* yr = y + row * ld_y;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        yr[i] = __fadd_rn(xr[i], b);
+}
+
+int launch_row_stat(scir_b200_ctx* ctx, int stat, const float* d_x, int64_t ld_x, int64_t batch, int64_t n, float* d_out)
+{
+    if (batch == 0) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+    if (batch > 0x7fffffffLL) return set_error(SCIR_B200_ERR_UNSUPPORTED, "too many rows");
+    const unsigned g = static_cast<unsigned>(batch);
+    if (stat == STAT_MEAN) row_stat_kernel<STAT_MEAN><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
+    else if (stat == STAT_MIN) row_stat_kernel<STAT_MIN><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
+    else row_stat_kernel<STAT_MAX><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
+    SCIR_CUDA(cudaGetLastError(), "row_stat_kernel launch");
+    ctx->launches++;
+    return SCIR_B200_OK;
+}
+
+int launch_row_offset(scir_b200_ctx* ctx, const float* d_x, int64_t ld_x, const float* d_bg, float sign, float* d_y,
+                      int64_t ld_y, int64_t batch, int64_t n)
+{
+    if (batch == 0 || n == 0) return SCIR_B200_OK;
+    SCIR_TRY(ctx_bind(ctx));
+    if (batch > 65535) return set_error(SCIR_B200_ERR_UNSUPPORTED, "row offset: more than 65535 rows per call");
+    const unsigned gx = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 64));
+    row_offset_kernel<<<dim3(gx, static_cast<unsigned>(batch)), 256, 0, ctx->stream>>>(d_x, ld_x, d_bg, sign, d_y, ld_y, n);
+    SCIR_CUDA(cudaGetLastError(), "row_offset_kernel launch");
+    ctx->launches++;
+    return SCIR_B200_OK;
+}
+
 }  // namespace scir_b200

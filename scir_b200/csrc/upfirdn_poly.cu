@@ -22,6 +22,7 @@
 //   * outputs go back through shared memory and one bulk store.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "upfirdn_ext.cuh"
 
 #include <algorithm>
 
@@ -46,6 +47,7 @@ struct PolyParams {
     long long ntiles;
     int nchunk;
     int in_vec_ok, out_vec_ok;
+    ExtSpec ext;                  // value of samples outside [0, n_in) (edge tiles only)
 };
 
 // ---- packed FP32 (FFMA2) form ------------------------------------------------------------------------
@@ -241,10 +243,7 @@ upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant_
         __syncthreads();
         mbar_wait(bar, 0);
     } else {
-        for (int s = tid; s < len; s += NT) {
-            const long long xi = a + s;
-            smem[s] = (xi >= 0 && xi < q.n_in) ? xr[xi] : 0.f;      // mode='constant', cval 0
-        }
+        for (int s = tid; s < len; s += NT) smem[s] = upfirdn_sample(xr, a + s, q.n_in, q.ext);
         __syncthreads();
     }
 
@@ -350,11 +349,8 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
         if (can_bulk(a)) {
             mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
             phases ^= 1u << s;
-        } else {                                           // edge tile: mode='constant', cval 0
-            for (int t = tid; t < len; t += NT) {
-                const long long xi = a + t;
-                in[t] = (xi >= 0 && xi < q.n_in) ? xr[xi] : 0.f;
-            }
+        } else {                                           // edge tile: samples outside the row by extension mode
+            for (int t = tid; t < len; t += NT) in[t] = upfirdn_sample(xr, a + t, q.n_in, q.ext);
             __syncthreads();
         }
 
@@ -480,7 +476,7 @@ constexpr RateGeom kRates[] = {
 
 int launch_upfirdn_poly(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up, int64_t down,
                         const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y, int64_t ld_y,
-                        int64_t m_begin, int64_t m_count, bool* handled)
+                        int64_t m_begin, int64_t m_count, ExtSpec ext, bool* handled)
 {
     *handled = false;
     constexpr int KCP = 32;
@@ -511,6 +507,7 @@ int launch_upfirdn_poly(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64
     PolyParams q{};
     q.x = d_x; q.y = d_y; q.ld_x = ld_x; q.ld_y = ld_y; q.n_in = n_in;
     q.m_begin = m_begin; q.m_end = m_begin + m_count;
+    q.ext = ext;
     const int64_t step = 4 * up;
     q.base_m = (m_begin / step) * step;
     const int64_t tile_out = static_cast<int64_t>(kPolyNT) * up * g;

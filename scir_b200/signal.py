@@ -133,13 +133,26 @@ def upfirdn_output_len(len_h, in_len, up, down) -> int:
     return int(_load().scir_b200_upfirdn_out_len(int(len_h), int(in_len), int(up), int(down)))
 
 
-def upfirdn(h, x, up=1, down=1, *, ctx=None):
-    """upfirdn(h, x, up, down, mode='constant') along the last axis; f32 in, f32 out."""
+UPFIRDN_MODES = {"constant": L.EXT_CONSTANT, "symmetric": L.EXT_SYMMETRIC, "edge": L.EXT_EDGE, "smooth": L.EXT_SMOOTH,
+                 "wrap": L.EXT_PERIODIC, "reflect": L.EXT_REFLECT, "antisymmetric": L.EXT_ANTISYMMETRIC,
+                 "antireflect": L.EXT_ANTIREFLECT, "line": L.EXT_LINE}       # mode_enum, _upfirdn_apply.pyx:89-105
+
+
+def _mode_code(mode):
+    try:
+        return UPFIRDN_MODES[mode]
+    except (KeyError, TypeError):
+        raise ValueError(f"Unknown mode: {mode}") from None                  # pyx:104
+
+
+def upfirdn(h, x, up=1, down=1, mode="constant", cval=0.0, *, ctx=None):
+    """upfirdn(h, x, up, down, mode, cval) along the last axis (scipy/signal/_upfirdn.py:107-216); f32 in, f32 out."""
     if int(up) != up or int(down) != down:
         raise ValueError("up and down must be integers")                     # _upfirdn.py:95-97
     up, down = int(up), int(down)
     if up < 1 or down < 1:
         raise ValueError("Both up and down must be >= 1")                    # _upfirdn.py:98
+    m = _mode_code(mode)
     ht = _taps_f32(h)
     x2, was1d = _as_2d(x)
     dev, xo, xp, ld, batch, n, c = _prep(x2)
@@ -149,14 +162,14 @@ def upfirdn(h, x, up=1, down=1, *, ctx=None):
     lo = upfirdn_output_len(ht.size, n, up, down)
     if dev:
         y, yp, ldy = _alloc_like(dev, xo, batch, lo)
-        _check(_load().scir_b200_upfirdn_f32(c.handle, _ptr(ht), ht.size, up, down, xp, ld, batch, n, yp, ldy,
-                                             0, lo))
+        _check(_load().scir_b200_upfirdn_mode_f32(c.handle, _ptr(ht), ht.size, up, down, m, float(cval), xp, ld, batch, n,
+                                                  yp, ldy, 0, lo))
         return y[0] if was1d else y
     y = np.empty((batch, lo), dtype=np.float32)
     bx, by = _DevBuf(c, xo.nbytes).upload(xo), _DevBuf(c, y.nbytes)
     try:
-        _check(_load().scir_b200_upfirdn_f32(c.handle, _ptr(ht), ht.size, up, down, bx.p, ld, batch, n, by.p,
-                                             max(lo, 1), 0, lo))
+        _check(_load().scir_b200_upfirdn_mode_f32(c.handle, _ptr(ht), ht.size, up, down, m, float(cval), bx.p, ld, batch, n,
+                                                  by.p, max(lo, 1), 0, lo))
         c.sync()
         by.download(y)
     finally:
@@ -185,13 +198,26 @@ def kaiser_lowpass(up: int, down: int) -> np.ndarray:
     return (h / h.sum()).astype(np.float64)
 
 
-def resample_poly(x, up, down, window=("kaiser", 5.0), *, ctx=None):
-    """resample_poly(x, up, down, window) along the last axis, padtype='constant' (cval 0)."""
+_PAD_STATS = {"mean": L.PAD_STAT_MEAN, "median": L.PAD_STAT_MEDIAN, "minimum": L.PAD_STAT_MINIMUM,
+              "maximum": L.PAD_STAT_MAXIMUM}
+
+
+def resample_poly(x, up, down, window=("kaiser", 5.0), padtype="constant", cval=None, *, ctx=None):
+    """resample_poly(x, up, down, window, padtype, cval) along the last axis (scipy/signal/_signaltools.py:3865-3957).
+    padtype: an upfirdn extension mode, or 'mean' / 'minimum' / 'maximum' ('median' raises: no device kernel yet)."""
     if int(up) != up or int(down) != down:
         raise ValueError("up and down must be integers")
     up, down = int(up), int(down)
     if up < 1 or down < 1:
         raise ValueError("up and down must be >= 1")                         # :3876-3877
+    if cval is not None and padtype != "constant":
+        raise ValueError("cval has no effect when padtype is " + str(padtype))   # :3878-3879
+    if padtype in _PAD_STATS:
+        code = _PAD_STATS[padtype]
+    elif padtype in UPFIRDN_MODES:
+        code = UPFIRDN_MODES[padtype]
+    else:
+        raise ValueError("padtype must be one of: " + ", ".join(list(UPFIRDN_MODES) + list(_PAD_STATS)))   # :3932-3934
     if isinstance(window, (tuple, str)):
         if window != ("kaiser", 5.0):
             raise GpuError.backend_unavailable("pass the filter as an array; only the default "
@@ -203,9 +229,27 @@ def resample_poly(x, up, down, window=("kaiser", 5.0), *, ctx=None):
     c = ctx or c
     plan = resample_poly_plan(n, w.size, up, down)
     n_out = n if (plan["up"] == 1 and plan["down"] == 1) else plan["n_out"]
-    y, yp, ldy = _alloc_like(dev, xo, batch, n_out)
-    fn = _load().scir_b200_resample_poly_f32 if dev else _load().scir_b200_resample_poly_f32_host
-    _check(fn(c.handle, _ptr(w), w.size, up, down, xp, ld, batch, n, yp, ldy))
+    plain = (code == L.EXT_CONSTANT and not cval)
+    if dev or plain:
+        y, yp, ldy = _alloc_like(dev, xo, batch, n_out)
+        if plain:
+            fn = _load().scir_b200_resample_poly_f32 if dev else _load().scir_b200_resample_poly_f32_host
+            _check(fn(c.handle, _ptr(w), w.size, up, down, xp, ld, batch, n, yp, ldy))
+        else:
+            _check(_load().scir_b200_resample_poly_pad_f32(c.handle, _ptr(w), w.size, up, down, code, float(cval or 0.0),
+                                                           xp, ld, batch, n, yp, ldy))
+        return y[0] if was1d else y
+    # host arrays with a non-default padtype: library-owned device buffers around the device entry point
+    y = np.empty((batch, n_out), dtype=np.float32)
+    bx, by = _DevBuf(c, xo.nbytes).upload(xo), _DevBuf(c, y.nbytes)
+    try:
+        _check(_load().scir_b200_resample_poly_pad_f32(c.handle, _ptr(w), w.size, up, down, code, float(cval or 0.0),
+                                                       bx.p, ld, batch, n, by.p, max(n_out, 1)))
+        c.sync()
+        by.download(y)
+    finally:
+        bx.free()
+        by.free()
     return y[0] if was1d else y
 
 

@@ -378,6 +378,89 @@ def test_upfirdn_tile_kernel_is_the_one_that_runs():
     assert ctx.get_option("poly_launches") == p0 + 1
 
 
+# ---- signal-extension modes (_upfirdn_apply.pyx:110-231) -----------------------------------
+MODES = ["constant", "symmetric", "edge", "smooth", "wrap", "reflect", "antisymmetric", "antireflect", "line"]
+
+
+@pytest.fixture(scope="module")
+def scipy_modes(golden_dir):
+    return np.load(os.path.join(golden_dir, "scipy_modes.npz"))
+
+
+def test_upfirdn_modes_golden(scipy_modes):
+    """All nine modes against SciPy's outputs (committed golden vectors), host and device arrays, including inputs
+    shorter than the filter's reach (multiple reflections)."""
+    v = scipy_modes
+    for i, (lh, lx, up, down) in enumerate(v["cases"]):
+        h, x = v[f"u{i}_h"], v[f"u{i}_x"]
+        for m in MODES:
+            want = v[f"u{i}_{m}"]
+            scale = max(np.abs(want).max() / max(np.abs(h).sum(), 1e-30), np.abs(x).max())     # extension can exceed max|x|
+            for xin in (x, dev(x)):
+                y = signal.upfirdn(h, xin, int(up), int(down), mode=m)
+                y = y.cpu().numpy() if hasattr(y, "cpu") else y
+                assert y.shape == want.shape and y.dtype == np.float32
+                assert np.abs(y - want).max() <= tol(h, np.asarray([scale]), 2.0), (i, m)
+        y = signal.upfirdn(h, dev(x), int(up), int(down), mode="constant", cval=0.75).cpu().numpy()
+        assert np.abs(y - v[f"u{i}_constant_cval"]).max() <= tol(h, x, 2.0)
+    with pytest.raises(ValueError):
+        signal.upfirdn(np.ones(3, np.float32), np.ones(5, np.float32), 1, 1, mode="bogus")
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("up,down,len_h,n", [(3, 2, 97, 30000), (2, 3, 64, 40001), (1, 2, 33, 25000), (5, 3, 41, 9000),
+                                            (4, 1, 40, 12000)])
+def test_upfirdn_modes_vs_oracle_many_tiles(mode, up, down, len_h, n):
+    """Tile kernels (rates in the template grid) and the generic kernel (5/3) at sizes with interior tiles: only the
+    edge tiles may see the mode."""
+    rng = np.random.RandomState(up * 100 + down + len_h)
+    h = rng.randn(len_h).astype(np.float32)
+    x = (rng.rand(3, n).astype(np.float32) * 2 - 1)
+    want = O.upfirdn_mode(h, x, up, down, mode, 0.0)
+    y = signal.upfirdn(h, dev(x), up, down, mode=mode).cpu().numpy()
+    assert y.shape == want.shape
+    scale = max(np.abs(want).max() / np.abs(h).sum(), 1.0)
+    assert np.abs(y - want).max() <= tol(h, np.asarray([scale]), 2.0)
+    # interior outputs do not depend on the mode at all
+    y0 = signal.upfirdn(h, dev(x), up, down).cpu().numpy()
+    lo, hi = (len_h // down) + 2, y.shape[1] - (len_h // down) - 2 - (len_h * 1) // down
+    assert np.array_equal(y[:, lo:hi], y0[:, lo:hi])
+
+
+def test_resample_poly_padtypes_golden(scipy_modes):
+    v = scipy_modes
+    for i, (up, down, lh, n) in enumerate(v["rcases"]):
+        h, x = v[f"r{i}_h"], v[f"r{i}_x"]
+        for pt in [str(s) for s in v["padtypes"]]:
+            if pt == "median":
+                with pytest.raises(gpu.GpuError):
+                    signal.resample_poly(dev(x), int(up), int(down), h, padtype=pt)
+                continue
+            want = v[f"r{i}_{pt}"]
+            for xin in (x, dev(x)):
+                y = signal.resample_poly(xin, int(up), int(down), h, padtype=pt)
+                y = y.cpu().numpy() if hasattr(y, "cpu") else y
+                assert y.shape == want.shape
+                assert np.abs(y - want).max() <= tol(h * up, x, 4.0), (i, pt)
+        y = signal.resample_poly(dev(x), int(up), int(down), h, padtype="constant", cval=0.5).cpu().numpy()
+        assert np.abs(y - v[f"r{i}_constant_cval"]).max() <= tol(h * up, x, 4.0)
+    with pytest.raises(ValueError):
+        signal.resample_poly(np.ones(8, np.float32), 2, 1, np.ones(5, np.float32), padtype="edge", cval=1.0)
+    with pytest.raises(ValueError):
+        signal.resample_poly(np.ones(8, np.float32), 2, 1, np.ones(5, np.float32), padtype="nope")
+
+
+def test_resample_poly_stat_padtypes_at_scale():
+    rng = np.random.RandomState(77)
+    from scipy.signal import firwin
+    h = firwin(96, 1.0 / 3.0, window=("kaiser", 5.0)).astype(np.float32)
+    x = (rng.rand(5, 50000).astype(np.float32) + 2.0)
+    for pt in ("mean", "minimum", "maximum", "line", "edge"):
+        want = O.resample_poly_padtype(x, 3, 2, h, pt)
+        y = signal.resample_poly(dev(x), 3, 2, h, padtype=pt).cpu().numpy()
+        assert np.abs(y - want).max() <= tol(h * 3, x, 4.0), pt
+
+
 def test_upfirdn_windowed_output():
     rng = np.random.RandomState(12)
     h = rng.randn(97).astype(np.float32)

@@ -293,3 +293,44 @@ def test_filtfilt_identity_and_short_input():
     np.testing.assert_allclose(O.filtfilt_fir(np.array([1.0], np.float32), x)[0], x[0], atol=1e-12)
     with pytest.raises(ValueError):
         O.filtfilt_fir(np.ones(5, np.float32), np.ones((1, 15), np.float32))   # n <= 3*ntaps
+
+
+# ---- signal-extension modes of upfirdn / resample_poly ------------------------------------
+@pytest.fixture(scope="module")
+def scipy_modes(golden_dir):
+    return np.load(os.path.join(golden_dir, "scipy_modes.npz"))
+
+
+def test_oracle_upfirdn_modes_pinned_on_scipy(scipy_modes):
+    """The C restatement of _extend_left / _extend_right / _apply_impl (_upfirdn_apply.pyx:110-231, :421-481)
+    against SciPy's own f64 outputs for all nine modes, including inputs shorter than the filter's reach."""
+    v = scipy_modes
+    for i, (lh, lx, up, down) in enumerate(v["cases"]):
+        h, x = v[f"u{i}_h"], v[f"u{i}_x"]
+        for m in [str(s) for s in v["modes"]]:
+            want = v[f"u{i}_{m}"]
+            got64 = O.upfirdn_mode(h, x, int(up), int(down), m, f64=True)          # all-f64 twin: to rounding
+            assert got64.shape == want.shape
+            np.testing.assert_allclose(got64, want, rtol=1e-12, atol=1e-12 * np.abs(h).sum() * np.abs(want).max())
+            got = O.upfirdn_mode(h, x, int(up), int(down), m)                       # f32 extension values, f64 sums
+            scale = np.abs(h.astype(np.float64)).sum() * max(np.abs(want).max(), 1.0)
+            assert np.abs(got - want).max() <= 1e-5 * scale, (i, m)
+        got = O.upfirdn_mode(h, x, int(up), int(down), "constant", 0.75, f64=True)
+        np.testing.assert_allclose(got, v[f"u{i}_constant_cval"], rtol=1e-12, atol=1e-12)
+    # mode='constant', cval=0 is the path every other test uses
+    h, x = v["u0_h"], v["u0_x"]
+    np.testing.assert_allclose(O.upfirdn_mode(h, x, 3, 2, "constant"), O.upfirdn(h, x, 3, 2), rtol=0, atol=0)
+
+
+def test_oracle_resample_poly_padtypes_pinned_on_scipy(scipy_modes):
+    v = scipy_modes
+    for i, (up, down, lh, n) in enumerate(v["rcases"]):
+        h, x = v[f"r{i}_h"], v[f"r{i}_x"]
+        for pt in [str(s) for s in v["padtypes"]]:
+            want = v[f"r{i}_{pt}"]
+            got = O.resample_poly_padtype(x, int(up), int(down), h, pt)
+            assert got.shape == want.shape
+            tol = 1e-5 * np.abs(h.astype(np.float64) * up).sum() * np.abs(x).max() * 4
+            assert np.abs(got - want).max() <= tol, (i, pt)
+        got = O.resample_poly_padtype(x, int(up), int(down), h, "constant", 0.5)
+        assert np.abs(got - v[f"r{i}_constant_cval"]).max() <= 1e-5 * np.abs(h * up).sum() * np.abs(x).max() * 4
