@@ -3,6 +3,8 @@
 // stands where the reference's `mod cuda` host wrappers stood (crates/scir-gpu/src/lib.rs:840-1113).
 #include "common.cuh"
 
+#include <cmath>
+
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -96,11 +98,29 @@ static int check_taps(const float* taps, int64_t k)
 //   * the FP32 direct family is FFMA-issue bound, time ~ K: at K = 63 it needs 2.40 ms for config 2 where
 //     the bytes alone take 1.31 ms;
 //   * the tcgen05 block-Toeplitz contraction (block-scaled FP16x3, error <= 3 * 2^-22 per product) runs the
-//     same launch in 1.54 ms and stays HBM-bound up to K ~ 130, so it takes over as soon as the direct
-//     kernel would leave the HBM roofline (K >= 48) -- provided the launch has at least one 128 x 128
-//     output tile per SM: below that its one-CTA-per-SM set-up (TMEM, Hankel tap arrays) is not amortised
-//     and the direct kernel's finer tiles win (config 1: 21 us vs 49 us);
-//   * long filters (K >= 1024) always take the tensor path: 17 ms vs the 118 ms FP32 roofline at K = 4097.
+//     same launch in 1.5 ms and stays HBM-bound up to K ~ 130 -- but it is one persistent CTA per SM with a
+//     ~40 us floor (TMEM allocation, Hankel tap arrays, a three-deep pipeline to fill, the fix-up launch;
+//     config 1: 49 us against the direct kernel's 20 us), and it works in whole 128 x 128 output tiles.
+// So both are costed with a small model (fitted to the sweep in profiles/README.md) and the cheaper one runs;
+// K >= toeplitz_min_k (1024) always takes the tensor path, where the direct kernel is 7x slower at any size
+// that matters.  The direct kernel's own streaming floor (~4.4 TB/s) means large launches go to the tensor
+// path even for short filters: there it is simply the better streaming kernel.
+static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t tiles)
+{
+    // fitted to tools/sweep_dispatch.py on B200 (45 shapes, K = 48 .. 511, 64 .. 16384 tiles; profiles/README.md):
+    //   direct:   14 us + per 16384 outputs max(30 ns [its streaming floor, ~4.4 TB/s], (2K + 40) flop / 66 TFLOP/s)
+    //   toeplitz: max(60 us, 30 us + rounds * max(3.2 us [HBM share of one tile per SM], 52 ns per MMA))
+    const double units = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch) / 16384.0;
+    const double t_direct = 14e-6 + units * std::max(30e-9, 16384.0 * (2.0 * static_cast<double>(k) + 40.0) / 66e12);
+    const int64_t pmax = (k - 1 + 127) / 128;
+    int64_t ksteps = 0;
+    for (int64_t pb = 0; pb <= pmax; ++pb) ksteps += 8 - (std::max<int64_t>(0, 128 * pb - (k - 1)) >> 4);
+    const double t_round = std::max(3.2e-6, static_cast<double>(3 * ksteps) * 52e-9);
+    const double rounds = std::ceil(static_cast<double>(tiles) / static_cast<double>(ctx->sm_count));
+    const double t_toep = std::max(60e-6, 30e-6 + rounds * t_round);
+    return t_toep < t_direct;
+}
+
 int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
 {
     const int64_t mode = ctx->opt.long_tap_path;
@@ -108,7 +128,7 @@ int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t 
         int64_t tiles = 0;
         if (toeplitz_supported(ctx, pass, k, &tiles)) {
             const bool want = (mode == 2) || k >= ctx->opt.toeplitz_min_k ||
-                              (k >= ctx->opt.toeplitz_min_k_full && tiles >= ctx->sm_count);
+                              (k >= ctx->opt.toeplitz_min_k_full && prefer_toeplitz(ctx, pass, k, tiles));
             if (want) return launch_fir_toeplitz(ctx, pass, c, k);
         }
     }
@@ -408,6 +428,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "toeplitz_split")) return &o.toeplitz_split;
     if (!strcmp(key, "toeplitz_chains")) return &o.toeplitz_chains;
     if (!strcmp(key, "toeplitz_ts")) return &o.toeplitz_ts;
+    if (!strcmp(key, "toeplitz_stcs")) return &o.toeplitz_stcs;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;

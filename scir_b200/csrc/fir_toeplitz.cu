@@ -94,6 +94,7 @@ struct ToepParams {
     unsigned buf_bytes;                 // one buffer (multiple of 128)
     float tap_scale, tap_inv;           // power of two applied to the taps (fmt 0) and its inverse
     int* tile_flags;                    // [total_tiles]: 1 if the tile's slab held a NaN / Inf sample (see toeplitz_fixup_kernel)
+    int stream_stores;                  // 1: epilogue stores carry the evict-first hint (st.global.cs): outputs are written once
 };
 
 // ---- tcgen05 / TMEM PTX ----------------------------------------------------------------------------------
@@ -675,7 +676,15 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
                 const long long ipb = (j0 + c4 * 32) * TB + rr - q.org;
                 if (interior) {                            // one base pointer, immediate offsets, no guards
                     float* yb = yr + map_index(p, ipb);
-                    if (p.dir > 0) {
+                    if (q.stream_stores) {
+                        if (p.dir > 0) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) __stcs(yb + c * TB, __uint_as_float(v[c]) * inv_x * inv_c);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) __stcs(yb - c * TB, __uint_as_float(v[c]) * inv_x * inv_c);
+                        }
+                    } else if (p.dir > 0) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) yb[c * TB] = __uint_as_float(v[c]) * inv_x * inv_c;
                     } else {
@@ -760,6 +769,7 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
     q.terms = static_cast<int>(terms);
     q.nver = (terms == 6) ? 3 : 2;
     q.chains = (ctx->opt.toeplitz_chains == 2) ? 2 : 1;
+    q.stream_stores = (ctx->opt.toeplitz_stcs != 0) ? 1 : 0;
     {   // TMEM: 2 accumulator stages x chains x 128 columns, then as many Toeplitz blocks (64 columns per split term)
         // as fit in the 512 columns; blocks beyond that stay shared-memory operands
         const int acc_cols = 2 * TN * q.chains;
