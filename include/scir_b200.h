@@ -107,6 +107,15 @@ SCIR_B200_API int scir_b200_fir1d_batched_f32_host(scir_b200_ctx *ctx,
                                      float *h_y, int64_t ld_y,
                                      int64_t batch, int64_t n);
 
+/* f64 twin on device-resident data: fir1d_batched_f64 (lib.rs:1166-1184; the reference has it on the CPU only,
+ * as the high-precision companion its tests compare with, :1263-1298).  Same definition, IEEE f64 products and
+ * sums (DFMA), newest sample first.  k <= ~23000 taps (shared-memory tile). */
+SCIR_B200_API int scir_b200_fir1d_batched_f64(scir_b200_ctx *ctx,
+                                const double *d_x, int64_t ld_x,
+                                const double *taps, int64_t k, int tap_order,
+                                double *d_y, int64_t ld_y,
+                                int64_t batch, int64_t n);
+
 /* ---- scir-signal FIR routes that map onto the hot path (SciPy is the spec) ---- */
 
 /* lfilter(b, [a0], x) with optional streaming state (scipy/signal/_signaltools.py:2181-2242).

@@ -53,6 +53,7 @@ SIGNATURES = {
     "scir_b200_host_free": (C.c_int, [vp]),
     "scir_b200_fir1d_batched_f32": (C.c_int, [vp, fp, i64, fp, i64, C.c_int, fp, i64, i64, i64]),
     "scir_b200_fir1d_batched_f32_host": (C.c_int, [vp, fp, i64, fp, i64, C.c_int, fp, i64, i64, i64]),
+    "scir_b200_fir1d_batched_f64": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, vp, i64, i64, i64]),
     "scir_b200_lfilter_fir_f32": (C.c_int, [vp, fp, i64, C.c_float, fp, i64, fp, fp, fp, i64, i64, i64]),
     "scir_b200_upfirdn_out_len": (i64, [i64, i64, i64, i64]),
     "scir_b200_upfirdn_f32": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64, i64, i64]),

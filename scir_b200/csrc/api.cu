@@ -728,6 +728,21 @@ int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx* ctx, const float* b, int64_t 
                          });
 }
 
+int scir_b200_fir1d_batched_f64(scir_b200_ctx* ctx, const double* d_x, int64_t ld_x, const double* taps, int64_t k,
+                                int tap_order, double* d_y, int64_t ld_y, int64_t batch, int64_t n)
+{
+    SCIR_TRY(check_ctx(ctx));
+    if (taps == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "taps is NULL");
+    if (k < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "need at least one tap (k=%lld)", (long long)k);
+    if (tap_order != SCIR_B200_TAPS_SCIR && tap_order != SCIR_B200_TAPS_LFILTER)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
+    SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
+    SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    std::vector<double> c(static_cast<size_t>(k));
+    for (int64_t d = 0; d < k; ++d) c[static_cast<size_t>(d)] = (tap_order == SCIR_B200_TAPS_SCIR) ? taps[k - 1 - d] : taps[d];
+    return launch_fir_f64(ctx, d_x, ld_x, c.data(), k, d_y, ld_y, batch, n);
+}
+
 // ---- DeviceArray elementwise ops on device-resident f32 (lib.rs:268-377 dispatch, :840-1034 CUDA wrappers) ----
 static int check_vec(const void* p, int64_t n, const char* name)
 {

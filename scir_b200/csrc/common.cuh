@@ -128,6 +128,10 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
 
 int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);
 
+// ---- f64 twin of the hot path (fir_f64.cu); taps by delay index, host pointer -----------------------------
+int launch_fir_f64(scir_b200_ctx* ctx, const double* d_x, int64_t ld_x, const double* taps_by_delay, int64_t k, double* d_y,
+                   int64_t ld_y, int64_t batch, int64_t n);
+
 // ---- DeviceArray elementwise ops (elementwise.cu): op 0 add-scalar, 1 mul-scalar, 2 add ------------------
 int launch_elementwise(scir_b200_ctx* ctx, int op, const float* d_a, const float* d_b, float alpha, float* d_y, int64_t n);
 // per-row mean (0) / minimum (1) / maximum (2), and y = x + sign * bg[row]

@@ -202,6 +202,43 @@ def fir1d_batched_f32_cuda(x, taps, *, ctx: Context | None = None, out=None,
     return y
 
 
+def fir1d_batched_f64_cuda(x, taps, *, ctx: Context | None = None, tap_order: int = L.TAPS_SCIR):
+    """Device twin of fir1d_batched_f64 (lib.rs:1166-1184): x is a 2-D float64 CUDA tensor (result: same) or a
+    float64 numpy array (uploaded, filtered, downloaded)."""
+    lib = _load()
+    t = np.ascontiguousarray(taps, dtype=np.float64)
+    if t.ndim != 1 or t.size < 1:
+        raise GpuError.shape_mismatch("taps must be 1-D with at least one element")
+    if _is_torch(x):
+        import torch
+        if x.dtype != torch.float64 or x.dim() != 2 or not x.is_cuda:
+            raise GpuError.shape_mismatch("device input must be a 2-D float64 CUDA tensor")
+        xt = x.contiguous()
+        c = ctx or torch_context(xt)
+        y = torch.empty_like(xt)
+        b, n = xt.shape
+        _check(lib.scir_b200_fir1d_batched_f64(c.handle, xt.data_ptr(), max(n, 1), _ptr(t), t.size, tap_order,
+                                               y.data_ptr(), max(n, 1), b, n))
+        return y
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    if a.ndim != 2:
+        raise GpuError.shape_mismatch("x must be 2-D (batch, n)")
+    c = ctx or default_context(0)
+    b, n = a.shape
+    y = np.empty_like(a)
+    px, py = C.c_void_p(), C.c_void_p()
+    _check(lib.scir_b200_malloc(c.handle, max(a.nbytes, 8), C.byref(px)))
+    _check(lib.scir_b200_malloc(c.handle, max(a.nbytes, 8), C.byref(py)))
+    try:
+        _check(lib.scir_b200_memcpy_h2d(c.handle, px, _ptr(a), a.nbytes))
+        _check(lib.scir_b200_fir1d_batched_f64(c.handle, px, max(n, 1), _ptr(t), t.size, tap_order, py, max(n, 1), b, n))
+        _check(lib.scir_b200_memcpy_d2h(c.handle, _ptr(y), py, y.nbytes))
+    finally:
+        lib.scir_b200_free(c.handle, px)
+        lib.scir_b200_free(c.handle, py)
+    return y
+
+
 def fir1d_batched_f32_auto(x, taps, device: Device, **kw):
     """lib.rs:515-531, minus the silent fallback."""
     if device == Device.Cuda:

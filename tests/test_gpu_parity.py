@@ -617,6 +617,31 @@ def test_device_array_roundtrip_and_chained_fir():
 
 
 # ---- multi-GPU front end (needs >= 2 devices) ------------------------------------------------------------
+def test_fir_f64_device_twin():
+    """fir1d_batched_f64 (lib.rs:1166-1184) on the device: the reference's own random property test
+    (3 x 32, k = 5, taps 1/(i+1), atol = rtol = 1e-12: lib.rs:1263-1298), the doc-test shape (:1160-1164), then
+    shapes with halos, many tiles, long filters and both tap orders against the f64 oracle."""
+    rng = np.random.RandomState(1)
+    x = rng.rand(3, 32) * 2 - 1
+    taps = 1.0 / (np.arange(5, dtype=np.float64) + 1.0)
+    y = gpu.fir1d_batched_f64_cuda(x, taps)
+    np.testing.assert_allclose(y, O.fir1d_batched_f64(x, taps), atol=1e-12, rtol=1e-12)
+    y = gpu.fir1d_batched_f64_cuda(np.array([[1.0, 2.0, 3.0, 4.0]]), np.array([0.25, 0.5, 0.25]))
+    np.testing.assert_allclose(y, [[0.25, 1.0, 2.0, 3.0]], atol=1e-15)
+    for b, n, k in ((2, 5000, 63), (3, 2048, 1), (1, 2049, 300), (4, 10000, 4097), (2, 7, 20)):
+        x = rng.randn(b, n)
+        taps = rng.randn(k)
+        want = O.fir1d_batched_f64(x, taps)
+        yd = gpu.fir1d_batched_f64_cuda(torch.from_numpy(x).cuda(), taps)
+        assert yd.dtype == torch.float64
+        scale = np.abs(taps).sum() * np.abs(x).max()
+        assert np.abs(yd.cpu().numpy() - want).max() <= 1e-13 * scale, (b, n, k)
+        yl = gpu.fir1d_batched_f64_cuda(x, taps[::-1].copy(), tap_order=L.TAPS_LFILTER)
+        assert np.abs(yl - want).max() <= 1e-13 * scale
+    with pytest.raises(gpu.GpuError):
+        gpu.fir1d_batched_f64_cuda(torch.zeros((2, 8), device="cuda"), taps)        # f32 tensor: wrong dtype
+
+
 def test_device_array_elementwise_ops_bit_exact():
     """add_scalar_auto / mul_scalar_auto / add_auto (lib.rs:268-377) on device-resident arrays: the reference's
     doc-test vectors (lib.rs:258-262, :293-298, :345-350), then random data of awkward lengths bit-exact against
