@@ -103,15 +103,15 @@ static int check_taps(const float* taps, int64_t k)
 //     config 1: 49 us against the direct kernel's 20 us), and it works in whole 128 x 128 output tiles.
 // So both are costed with a small model (fitted to the sweep in profiles/README.md) and the cheaper one runs;
 // K >= toeplitz_min_k (1024) always takes the tensor path, where the direct kernel is 7x slower at any size
-// that matters.  The direct kernel's own streaming floor (~4.4 TB/s) means large launches go to the tensor
+// that matters.  The direct kernel's own streaming floor (~5.2 TB/s) means large launches go to the tensor
 // path even for short filters: there it is simply the better streaming kernel.
 static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t tiles)
 {
     // fitted to tools/sweep_dispatch.py on B200 (45 shapes, K = 48 .. 511, 64 .. 16384 tiles; profiles/README.md):
-    //   direct:   14 us + per 16384 outputs max(30 ns [its streaming floor, ~4.4 TB/s], (2K + 40) flop / 66 TFLOP/s)
+    //   direct:   14 us + per 16384 outputs max(25 ns [its streaming floor, ~5.2 TB/s], (2K + 29) flop / 72 TFLOP/s)
     //   toeplitz: max(60 us, 30 us + rounds * max(3.2 us [HBM share of one tile per SM], 52 ns per MMA))
     const double units = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch) / 16384.0;
-    const double t_direct = 14e-6 + units * std::max(30e-9, 16384.0 * (2.0 * static_cast<double>(k) + 40.0) / 66e12);
+    const double t_direct = 14e-6 + units * std::max(25e-9, 16384.0 * (2.0 * static_cast<double>(k) + 29.0) / 72e12);
     const int64_t pmax = (k - 1 + 127) / 128;
     int64_t ksteps = 0;
     for (int64_t pb = 0; pb <= pmax; ++pb) ksteps += 8 - (std::max<int64_t>(0, 128 * pb - (k - 1)) >> 4);
@@ -429,6 +429,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "toeplitz_chains")) return &o.toeplitz_chains;
     if (!strcmp(key, "toeplitz_ts")) return &o.toeplitz_ts;
     if (!strcmp(key, "toeplitz_stcs")) return &o.toeplitz_stcs;
+    if (!strcmp(key, "ffma2")) return &o.ffma2;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;

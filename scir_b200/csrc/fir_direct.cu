@@ -34,9 +34,14 @@
 
 namespace scir_b200 {
 
+constexpr int kPackedMaxK = 256;      // instantiations up to this many taps carry the shifted copy and use FFMA2
+
 template <int MAXK>
 struct TapsParam {
     float c[MAXK];
+    // c1[i] = c[i+1]: makes the tap pair (c[d], c[d+1]) an aligned 64-bit constant load for odd d too (fir_core2).
+    // Only the short-filter instantiations carry it (the 7936-tap one would not fit the 32 KB parameter space).
+    float c1[(MAXK <= kPackedMaxK) ? MAXK : 2];
 };
 
 struct FirTileParams {
@@ -45,6 +50,7 @@ struct FirTileParams {
     long long ntiles;     // tiles per row
     int nchunk;           // tap chunks (halo = nchunk * KC)
     int k;                // true tap count (non-finite redo)
+    int packed;           // 1: FFMA2 core (fir_core2), 0: scalar FFMA core (A/B: ctx option "ffma2" = 0)
     int in_vec_ok;        // input rows are 16-B aligned => interior tiles may use the bulk copy
     int out_vec_ok;       // same for the output side
 };
@@ -103,6 +109,78 @@ __device__ __forceinline__ void fir_core(float (&acc)[R], const float* wbase, in
             }
         }
     }
+}
+
+// ---- packed form of the same core (short-filter instantiations) ----------------------------------------------
+// sm_100's FFMA2 does two FMAs per issue slot: `FFMA2 Racc.F32x2, Rx.F32, URtaps.F32x2, Racc.F32x2` -- the sample
+// broadcast, two consecutive taps from a uniform-register pair, two consecutive outputs.  At the same FMA pipe
+// rate only half the issue slots are arithmetic, so LDS / LDCU / loop control stop costing FP32 throughput
+// (microbenchmark: 74.0 vs 67.7 TFLOP/s for the scalar stream).  Outputs (2p, 2p+1) of a thread share every
+// sample x[s]; their taps are (c[d], c[d+1]) (causal) or (c[d], c[d-1]) (anticausal): one aligned LDCU.64 from
+// `c` (even first index) or from the shifted copy `c1` (odd).  Where only one of the two outputs has a tap in
+// this chunk the other half multiplies by zero (a few percent of the instructions, at the chunk edges only).
+__device__ __forceinline__ void fma2_x(unsigned long long& acc, float x, float t0, float t1)
+{
+    unsigned long long xx, tt;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(tt) : "f"(t0), "f"(t1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(tt));
+}
+
+template <int KC, int R, int DIR, int MAXK>
+__device__ __forceinline__ void fir_core2(float (&acc)[R], const float* wbase, int nchunk, const TapsParam<MAXK>& taps)
+{
+    static_assert(R % 2 == 0 && KC % 2 == 0 && MAXK <= kPackedMaxK, "packed core geometry");
+    unsigned long long acc2[R / 2];
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) acc2[p] = 0ull;
+    for (int c = 0; c < nchunk; ++c) {
+        const float4* w = reinterpret_cast<const float4*>((DIR > 0) ? (wbase - (c + 1) * KC) : (wbase + c * KC));
+        const float* tc = taps.c + c * KC;
+        const float* tc1 = taps.c1 + c * KC;
+#pragma unroll
+        for (int v4 = 0; v4 < (KC + R) / 4; ++v4) {
+            const float4 v = w[v4];
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = 4 * v4 + e;
+#pragma unroll
+                for (int p = 0; p < R / 2; ++p) {
+                    // chunk-local delays of outputs 2p and 2p+1 for this sample
+                    const int d0 = (DIR > 0) ? (2 * p + KC - s) : (s - 2 * p);
+                    const int d1 = (DIR > 0) ? (d0 + 1) : (d0 - 1);
+                    const bool ok0 = d0 >= 0 && d0 < KC, ok1 = d1 >= 0 && d1 < KC;
+                    if (ok0 && ok1) {
+                        const int lo = (DIR > 0) ? d0 : d1;                    // the pair's lower tap index
+                        const float2 t = (lo % 2 == 0) ? *reinterpret_cast<const float2*>(tc + lo)
+                                                       : *reinterpret_cast<const float2*>(tc1 + lo - 1);
+                        if (DIR > 0) fma2_x(acc2[p], xv[e], t.x, t.y);
+                        else fma2_x(acc2[p], xv[e], t.y, t.x);
+                    } else if (ok0) {
+                        fma2_x(acc2[p], xv[e], tc[d0], 0.f);
+                    } else if (ok1) {
+                        fma2_x(acc2[p], xv[e], 0.f, tc[d1]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * p]), "=f"(acc[2 * p + 1]) : "l"(acc2[p]));
+}
+
+// dispatch: packed core where the instantiation carries the shifted tap copy
+template <int KC, int R, int DIR, int MAXK>
+__device__ __forceinline__ void fir_core_any(float (&acc)[R], const float* wbase, int nchunk, const TapsParam<MAXK>& taps, int packed)
+{
+    if constexpr (MAXK <= kPackedMaxK) {
+        if (packed) {
+            fir_core2<KC, R, DIR, MAXK>(acc, wbase, nchunk, taps);
+            return;
+        }
+    }
+    fir_core<KC, R, DIR, MAXK>(acc, wbase, nchunk, taps);
 }
 
 // Non-finite data: the tap array is zero-padded to whole chunks, and 0 * Inf = NaN would leak a stray Inf / NaN
@@ -174,7 +252,7 @@ fir_tile_kernel(const __grid_constant__ FirTileParams q, const __grid_constant__
     }
 
     float acc[R];
-    fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R), q.nchunk, taps);
+    fir_core_any<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R), q.nchunk, taps, q.packed);
 
     // ---- results back through shared memory, then one bulk store --------------------------------------
     if (any_nonfinite<R>(acc)) exact_redo<R, DIR, MAXK>(acc, (DIR > 0) ? (smem + DP + tid * R) : (smem + tid * R), q.k, taps);
@@ -292,7 +370,7 @@ fir_stream_kernel(const __grid_constant__ FirTileParams q, const __grid_constant
         }
 
         float acc[R];
-        fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.nchunk, taps);
+        fir_core_any<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.nchunk, taps, q.packed);
 
         if (tid == 0) bulk_store_wait_read<0>();           // the previous tile's store has drained `out`
         if (any_nonfinite<R>(acc)) exact_redo<R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.k, taps);
@@ -495,9 +573,15 @@ int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int6
     thread_local TapsParam<MAXK>* tl = nullptr;
     if (!tl) tl = new TapsParam<MAXK>();
     for (int i = 0; i < MAXK; ++i) tl->c[i] = (i < k) ? c[i] : 0.f;
+    if (MAXK <= kPackedMaxK)
+        for (int i = 0; i < MAXK; ++i) tl->c1[i] = (i + 1 < k) ? c[i + 1] : 0.f;
     const size_t len = static_cast<size_t>(q.nchunk) * KC + kTile;
-    // CTA-streaming for short filters (per-tile fixed costs matter), one tile per CTA for long ones
-    const bool stream = (ctx->opt.variant == 4) || (ctx->opt.variant != 3 && q.nchunk <= 2);
+    // One tile per CTA (4 CTAs/SM overlap each other's copies) is the default: with the packed FFMA2 core it beats the
+    // persistent CTA-streaming kernel at every size (profiles/r01_dispatch_sweep.txt: 10-20 % for K <= 128), whose
+    // two CTA barriers per tile are no longer hidden behind FFMA issue.  Streaming stays as the scalar-core default
+    // for short filters (ffma2=0) and as variant 4.
+    const bool packed = (MAXK <= kPackedMaxK && ctx->opt.ffma2 != 0);
+    const bool stream = (ctx->opt.variant == 4) || (ctx->opt.variant != 3 && q.nchunk <= 2 && !packed);
     const size_t smem_bytes = (stream ? (2 * len + kTile) : len) * sizeof(float);
     if (smem_bytes > static_cast<size_t>(ctx->max_smem_optin))
         return set_error(SCIR_B200_ERR_UNSUPPORTED, "tile needs %zu B of shared memory", smem_bytes);
@@ -528,6 +612,7 @@ int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int6
     }
     FirTileParams qq = q;
     qq.k = static_cast<int>(k);
+    qq.packed = (MAXK <= kPackedMaxK && ctx->opt.ffma2 != 0) ? 1 : 0;
     kern<<<static_cast<unsigned>(grid), kNT, smem_bytes, ctx->stream>>>(qq, *tl);
     SCIR_CUDA(cudaGetLastError(), "fir kernel launch");
     ctx->launches++;

@@ -26,13 +26,15 @@ def timeit(ctx, x, taps, reps=20):
 def main():
     shapes = [(64, 1 << 14), (16, 1 << 18), (64, 1 << 18), (256, 1 << 16), (256, 1 << 18), (1024, 1 << 16), (1024, 1 << 18),
               (32, 1 << 20), (128, 1 << 20)]
-    print(f"{'rows':>5} {'n':>8} {'K':>5} {'tiles':>6} {'direct us':>10} {'toeplitz us':>12} {'auto us':>9}  auto picks   best")
+    print(f"{'rows':>5} {'n':>8} {'K':>5} {'tiles':>6} {'direct us':>10} {'(tile us)':>10} {'toeplitz us':>12} {'auto us':>9}  auto picks   best")
     for rows, n in shapes:
         x = torch.rand((rows, n), device="cuda") * 2 - 1
         for k in (8, 31, 63, 127, 255, 511):
             taps = np.random.RandomState(k).randn(k).astype(np.float32)
-            d, t, a = gpu.Context(0), gpu.Context(0), gpu.Context(0)
+            d, t, a, v3 = gpu.Context(0), gpu.Context(0), gpu.Context(0), gpu.Context(0)
             d.set_option("long_tap_path", 1)
+            v3.set_option("variant", 3)                    # one tile per CTA (A/B arm of the direct family)
+            tv = timeit(v3, x, taps)
             t.set_option("long_tap_path", 2)
             td, tt = timeit(d, x, taps), timeit(t, x, taps)
             l0 = a.get_option("toeplitz_launches")
@@ -40,8 +42,8 @@ def main():
             picked = "toeplitz" if a.get_option("toeplitz_launches") > l0 else "direct"
             best = "toeplitz" if tt < td else "direct"
             flag = "" if picked == best or abs(tt - td) / min(tt, td) < 0.15 else "   <-- model wrong"
-            print(f"{rows:5d} {n:8d} {k:5d} {rows * ((n + 16383) // 16384):6d} {td:10.1f} {tt:12.1f} {ta:9.1f}  {picked:9s} {best}{flag}")
-            for c in (d, t, a):
+            print(f"{rows:5d} {n:8d} {k:5d} {rows * ((n + 16383) // 16384):6d} {td:10.1f} {tv:10.1f} {tt:12.1f} {ta:9.1f}  {picked:9s} {best}{flag}")
+            for c in (d, t, a, v3):
                 c.close()
 
 
