@@ -99,8 +99,8 @@ static int check_taps(const float* taps, int64_t k)
 //     the bytes alone take 1.31 ms;
 //   * the tcgen05 block-Toeplitz contraction (block-scaled FP16x3, error <= 3 * 2^-22 per product) runs the
 //     same launch in 1.5 ms and stays HBM-bound up to K ~ 130 -- but it is one persistent CTA per SM with a
-//     ~40 us floor (TMEM allocation, Hankel tap arrays, a three-deep pipeline to fill, the fix-up launch;
-//     config 1: 49 us against the direct kernel's 20 us), and it works in whole 128 x 128 output tiles.
+//     ~20 us floor (TMEM allocation, Hankel tap arrays, a three-deep pipeline to fill, the fix-up launch),
+//     and it works in whole 128 x 128 output tiles.
 // So both are costed with a small model (fitted to the sweep in profiles/README.md) and the cheaper one runs;
 // K >= toeplitz_min_k (1024) always takes the tensor path, where the direct kernel is 7x slower at any size
 // that matters.  The direct kernel's own streaming floor (~5.2 TB/s) means large launches go to the tensor
@@ -109,15 +109,15 @@ static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64
 {
     // fitted to tools/sweep_dispatch.py on B200 (45 shapes, K = 48 .. 511, 64 .. 16384 tiles; profiles/README.md):
     //   direct:   14 us + per 16384 outputs max(25 ns [its streaming floor, ~5.2 TB/s], (2K + 29) flop / 72 TFLOP/s)
-    //   toeplitz: max(60 us, 30 us + rounds * max(3.2 us [HBM share of one tile per SM], 52 ns per MMA))
+    //   toeplitz: max(20 us, 16 us + rounds * max(3.6 us [HBM share of one tile per SM], 58 ns per MMA))
     const double units = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch) / 16384.0;
     const double t_direct = 14e-6 + units * std::max(25e-9, 16384.0 * (2.0 * static_cast<double>(k) + 29.0) / 72e12);
     const int64_t pmax = (k - 1 + 127) / 128;
     int64_t ksteps = 0;
     for (int64_t pb = 0; pb <= pmax; ++pb) ksteps += 8 - (std::max<int64_t>(0, 128 * pb - (k - 1)) >> 4);
-    const double t_round = std::max(3.2e-6, static_cast<double>(3 * ksteps) * 52e-9);
+    const double t_round = std::max(3.6e-6, static_cast<double>(3 * ksteps) * 58e-9);
     const double rounds = std::ceil(static_cast<double>(tiles) / static_cast<double>(ctx->sm_count));
-    const double t_toep = std::max(60e-6, 30e-6 + rounds * t_round);
+    const double t_toep = std::max(20e-6, 16e-6 + rounds * t_round);
     return t_toep < t_direct;
 }
 
@@ -379,6 +379,7 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
     if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
     if (ctx->toep_flags.ptr) cudaFree(ctx->toep_flags.ptr);
     if (ctx->row_bg.ptr) cudaFree(ctx->row_bg.ptr);
+    if (ctx->toep_taps.ptr) cudaFree(ctx->toep_taps.ptr);
     for (int i = 0; i < 3; ++i) {
         if (ctx->stage_in[i].ptr) cudaFree(ctx->stage_in[i].ptr);
         if (ctx->stage_out[i].ptr) cudaFree(ctx->stage_out[i].ptr);

@@ -46,6 +46,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -65,10 +66,6 @@ constexpr int RQMAX = ((TN + kPmaxLimit) * 32 + kLoadThreads - 1) / kLoadThreads
 
 enum { MODE_REGISTER = 0, MODE_INPLACE = 1 };
 enum { FMT_F16_SCALED = 0, FMT_BF16 = 1 };
-
-struct ToepTaps {
-    float c[SCIR_B200_MAX_TAPS];        // by delay index, zero padded
-};
 
 struct ToepParams {
     FirPass p;
@@ -94,6 +91,9 @@ struct ToepParams {
     unsigned buf_bytes;                 // one buffer (multiple of 128)
     float tap_scale, tap_inv;           // power of two applied to the taps (fmt 0) and its inverse
     int* tile_flags;                    // [total_tiles]: 1 if the tile's slab held a NaN / Inf sample (see toeplitz_fixup_kernel)
+    const float* taps;                  // [k] by delay index, in device memory (ctx-owned, re-uploaded only when the filter
+                                        // changes): keeps the launch parameters at ~300 B -- 32 KB of by-value taps made the
+                                        // two launches of a pass cost 30-60 us of host time
     int stream_stores;                  // 1: epilogue stores carry the evict-first hint (st.global.cs): outputs are written once
 };
 
@@ -338,7 +338,7 @@ __device__ __forceinline__ void issue_tile(const ToepParams& q, bool leader, uin
 
 template <bool F16, int NVER>
 __global__ void __launch_bounds__(kToepThreads, 1)
-fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
+fir_toeplitz_kernel(const __grid_constant__ ToepParams q)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // raw_full[3] slab_full[3] buf_empty[3] acc_full[2] acc_empty[2]
@@ -392,7 +392,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
         for (int idx = tid; idx < q.hank_cores * 64; idx += kToepThreads) {
             const int u = idx >> 6, i = (idx >> 3) & 7, e = idx & 7;
             const int ci = top - (8 * u + i + e);
-            const float c = (ci >= 0 && ci < q.k) ? taps.c[ci] : 0.f;
+            const float c = (ci >= 0 && ci < q.k) ? __ldg(q.taps + ci) : 0.f;
             uint16_t h16, m16, l16;
             if constexpr (F16) {
                 const float cs = c * q.tap_scale;
@@ -716,7 +716,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q, const __grid_constant_
 // reference loop, crates/scir-gpu/src/lib.rs:1138-1150) do it: one FMA chain per output, so the non-finite value
 // reaches exactly the outputs whose window contains it.  Launched after every Toeplitz pass; with finite
 // data it reads total_tiles flags from L2 and exits (~3 us).
-__global__ void __launch_bounds__(256) toeplitz_fixup_kernel(const __grid_constant__ ToepParams q, const __grid_constant__ ToepTaps taps)
+__global__ void __launch_bounds__(256) toeplitz_fixup_kernel(const __grid_constant__ ToepParams q)
 {
     const FirPass& p = q.p;
     // 256 flags per CTA trip, one per thread (coalesced); the common case is one load and one barrier
@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(256) toeplitz_fixup_kernel(const __grid_consta
                 if (ip < q.ip_lo || ip >= q.ip_hi) continue;
                 const long long i = map_index(p, ip);                  // virtual index of this output
                 float acc = 0.f;
-                for (int d = 0; d < q.k; ++d) acc = fmaf(taps.c[d], tload(p, xr, p.dir > 0 ? i - d : i + d), acc);
+                for (int d = 0; d < q.k; ++d) acc = fmaf(__ldg(q.taps + d), tload(p, xr, p.dir > 0 ? i - d : i + d), acc);
                 yr[i] = acc;
             }
         }
@@ -852,10 +852,18 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
     if (!make_plan(ctx, pass, c, k, &plan))
         return set_error(SCIR_B200_ERR_UNSUPPORTED, "tcgen05 Toeplitz path cannot serve k=%lld", (long long)k);
     SCIR_TRY(ctx_bind(ctx));
-    thread_local ToepTaps* tl = nullptr;
-    if (!tl) tl = new ToepTaps();
-    for (int i = 0; i < SCIR_B200_MAX_TAPS; ++i) tl->c[i] = (i < k) ? c[i] : 0.f;
-    using Kern = void (*)(const ToepParams, const ToepTaps);
+    // taps live in a ctx-owned device buffer; upload only when the filter changed since the last launch
+    SCIR_TRY(ctx_scratch(ctx, ctx->toep_taps, static_cast<size_t>(SCIR_B200_MAX_TAPS) * sizeof(float)));
+    if (ctx->toep_taps_host.size() != static_cast<size_t>(k) ||
+        std::memcmp(ctx->toep_taps_host.data(), c, static_cast<size_t>(k) * sizeof(float)) != 0) {
+        ctx->toep_taps_host.assign(c, c + k);
+        // pageable source: the runtime stages it before returning, so `c` may be reused by the caller at once
+        SCIR_CUDA(cudaMemcpyAsync(ctx->toep_taps.ptr, ctx->toep_taps_host.data(), static_cast<size_t>(k) * sizeof(float),
+                                  cudaMemcpyHostToDevice, ctx->stream),
+                  "cudaMemcpyAsync(toeplitz taps)");
+    }
+    plan.q.taps = static_cast<const float*>(ctx->toep_taps.ptr);
+    using Kern = void (*)(const ToepParams);
     const bool f16 = (plan.q.fmt == FMT_F16_SCALED);
     const int flavour = (f16 ? 0 : 2) + (plan.q.nver > 2 ? 1 : 0);
     const Kern kerns[4] = {fir_toeplitz_kernel<true, 2>, fir_toeplitz_kernel<true, 3>, fir_toeplitz_kernel<false, 2>,
@@ -871,9 +879,9 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
     SCIR_TRY(ctx_scratch(ctx, ctx->toep_flags, static_cast<size_t>(plan.q.total_tiles) * sizeof(int)));
     plan.q.tile_flags = static_cast<int*>(ctx->toep_flags.ptr);
     const int grid = std::min(plan.q.total_tiles, ctx->sm_count);
-    kern<<<grid, kToepThreads, plan.smem_bytes, ctx->stream>>>(plan.q, *tl);
+    kern<<<grid, kToepThreads, plan.smem_bytes, ctx->stream>>>(plan.q);
     SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
-    toeplitz_fixup_kernel<<<std::min((plan.q.total_tiles + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(plan.q, *tl);
+    toeplitz_fixup_kernel<<<std::min((plan.q.total_tiles + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(plan.q);
     SCIR_CUDA(cudaGetLastError(), "fir_toeplitz_kernel launch");
     ctx->launches += 2;                                    // the contraction and its (normally idle) fix-up
     ctx->fixup_launches++;
