@@ -463,10 +463,10 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture of this command (profiles/); None until a capture exists for the config.
 TRAFFIC_PER_LAUNCH = {
-    "c2": 8.566e9,      # profiles/r01_c2_fir_toeplitz_kernel_v3.ncu.txt: 4.312 GB read + 4.254 GB written (algorithmic 8.590e9)
-    "c3": 8.544e9,      # profiles/r01_c3_fir_toeplitz_kernel.ncu.txt:    4.298 + 4.246            (algorithmic 8.590e9)
-    "c4": 21.451e9,     # profiles/r01_c4_upfirdn_stream_kernel.ncu.txt:  8.615 + 12.835           (algorithmic 21.475e9)
-    "c5": 17.229e9,     # profiles/r01_c5_fir_toeplitz_kernel.ncu.txt, per pass: 8.612 + 8.618     (algorithmic 17.180e9 per pass)
+    "c2": 8.576e9,      # profiles/r01_c2_fir_toeplitz_kernel_final.ncu.txt: 4.314 GB read + 4.262 GB written (algorithmic 8.590e9)
+    "c3": 8.543e9,      # profiles/r01_c3_fir_toeplitz_kernel_final.ncu.txt: 4.297 + 4.246           (algorithmic 8.590e9)
+    "c4": 21.450e9,     # profiles/r01_c4_upfirdn_stream_kernel_ffma2.ncu.txt: 8.612 + 12.838        (algorithmic 21.475e9)
+    "c5": 17.250e9,     # profiles/r01_c5_fir_toeplitz_kernel_final.ncu.txt, per pass: 8.616 + 8.634 (algorithmic 17.180e9 per pass)
 }
 
 if __name__ == "__main__":
