@@ -169,6 +169,34 @@ static int filtfilt_device(scir_b200_ctx* ctx, const float* b, int64_t k, int pa
     if (edge == 0) ext = EXT_NONE;
 
     const int64_t n_v = n + 2 * edge;
+
+    // ---- one pass instead of two ----------------------------------------------------------------------------
+    // With an extension of at least k-1 samples (SciPy's default is 3k) no kept output ever sees the held boundary
+    // of either pass: y[i] = sum_d b[d] * y1[i+d], y1[j] = sum_e b[e] * ext[j-e] with every index inside the
+    // extended signal, i.e. ONE zero-phase filter hc = b (*) flip(b) of 2k-1 taps over ext.  Same values to
+    // rounding (hc is formed in f64), half the HBM traffic, no intermediate matrix, and on the tensor path
+    // fewer MMAs than two k-tap passes (k = 255: 120 vs 144 per tile).  filtfilt_fused=0 keeps the two-pass form.
+    if (ext != EXT_NONE && edge >= k - 1 && 2 * k - 1 <= SCIR_B200_MAX_TAPS && ctx->opt.filtfilt_fused != 0 &&
+        (2 * k - 1 <= 4097 || k > 4097)) {
+        const int64_t kc = 2 * k - 1;
+        std::vector<float> hc(static_cast<size_t>(kc));
+        for (int64_t m = 0; m < kc; ++m) {                        // hc[m] = sum_j b[j] * b[j + (k-1) - m]
+            double acc = 0.0;
+            for (int64_t j = 0; j < k; ++j) {
+                const int64_t j2 = j + (k - 1) - m;
+                if (j2 >= 0 && j2 < k) acc += static_cast<double>(b[j]) * static_cast<double>(b[j2]);
+            }
+            hc[static_cast<size_t>(m)] = static_cast<float>(acc);
+        }
+        FirPass f{};                                              // causal 2k-1 taps, output delayed by k-1: centred
+        f.x = d_x; f.ld_x = ld_x; f.y = d_y; f.ld_y = ld_y; f.batch = batch;
+        f.n_x = n; f.n_v = n_v; f.in_off = -edge; f.out_off = -(edge + (k - 1));
+        f.out_begin = edge + (k - 1); f.out_end = edge + (k - 1) + n;
+        f.ext_mode = ext; f.bound = bound; f.dir = +1;
+        ctx->filtfilt_fused_calls++;
+        return launch_fir(ctx, f, hc.data(), kc);
+    }
+
     const int64_t padlead = (4 - edge % 4) % 4;                   // keeps both passes 16-B aligned
     const int64_t ld1 = (n_v + padlead + 3) / 4 * 4;
     SCIR_TRY(ctx_scratch(ctx, ctx->scratch, static_cast<size_t>(batch) * ld1 * sizeof(float)));
@@ -431,6 +459,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "toeplitz_ts")) return &o.toeplitz_ts;
     if (!strcmp(key, "toeplitz_stcs")) return &o.toeplitz_stcs;
     if (!strcmp(key, "ffma2")) return &o.ffma2;
+    if (!strcmp(key, "filtfilt_fused")) return &o.filtfilt_fused;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
@@ -456,6 +485,10 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
     }
     if (key && !strcmp(key, "fixup_launches")) {                   // read-only statistic
         *value = static_cast<int64_t>(ctx->fixup_launches);
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "filtfilt_fused_calls")) {                   // read-only statistic
+        *value = static_cast<int64_t>(ctx->filtfilt_fused_calls);
         return SCIR_B200_OK;
     }
     if (key && !strcmp(key, "poly_launches")) {                       // read-only statistic

@@ -38,6 +38,7 @@ struct Options {
     int64_t toeplitz_terms = 3; // split products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
     int64_t toeplitz_split = 0; // operand format of the split: 0 block-scaled FP16 (11-bit terms), 1 BF16 (8-bit terms)
     int64_t toeplitz_chains = 1; // accumulation chains per tile in TMEM (2: consecutive MMAs alternate accumulators; measured: no gain)
+    int64_t filtfilt_fused = 1;  // padded filtfilt as ONE zero-phase pass with b (*) flip(b) when the pad covers k-1 samples (0: two passes)
     int64_t ffma2 = 1;           // FP32 direct kernels, K <= 256: packed FFMA2 core (0: scalar FFMA, the A/B arm)
     int64_t toeplitz_stcs = 0;   // 1: evict-first hint on the epilogue's output stores (A/B)
     int64_t toeplitz_ts = 1;     // 1: keep the first Toeplitz blocks in TMEM (A operand from TMEM); 0: all operands from shared memory
@@ -62,6 +63,7 @@ struct scir_b200_ctx {
     int max_smem_optin = 0;
     uint64_t launches = 0;
     uint64_t toeplitz_launches = 0;        // launches served by the tcgen05 Toeplitz kernel
+    uint64_t filtfilt_fused_calls = 0;     // filtfilt calls served by the single-pass form
     uint64_t fixup_launches = 0;           // non-finite fix-up kernels (one after every FIR launch; idle on finite data)
     uint64_t poly_launches = 0;            // launches served by the polyphase TILE kernel (tests)
     scir_b200::Options opt;

@@ -578,6 +578,31 @@ def test_filtfilt_vs_oracle_random(batch, n, k, padtype):
     assert np.abs(yz - O.filtfilt_fir_nopad(b, x)).max() <= 1e-5 * s * s * 2
 
 
+@pytest.mark.parametrize("padtype", ["odd", "even", "constant"])
+def test_filtfilt_single_pass_equals_two_pass(padtype):
+    """Padded filtfilt runs as one zero-phase pass with b (*) flip(b) when the pad covers k-1 samples; a shorter
+    pad (padlen < k-1) must fall back to two passes.  Both against the oracle, and against each other."""
+    rng = np.random.RandomState(12)
+    from scipy.signal import firwin
+    b = firwin(63, 0.3).astype(np.float32)
+    x = (rng.rand(4, 30000).astype(np.float32) * 2 - 1)
+    code = {"odd": O.PAD_ODD, "even": O.PAD_EVEN, "constant": O.PAD_CONSTANT}[padtype]
+    hc = np.convolve(b.astype(np.float64), b[::-1].astype(np.float64))
+    for padlen in (None, 62, 61, 10):
+        one, two = gpu.Context(0), gpu.Context(0)
+        two.set_option("filtfilt_fused", 0)
+        y1 = signal.filtfilt(b, [1.0], dev(x), padtype=padtype, padlen=padlen, ctx=one)
+        y2 = signal.filtfilt(b, [1.0], dev(x), padtype=padtype, padlen=padlen, ctx=two)
+        one.sync(); two.sync()
+        fused = one.get_option("filtfilt_fused_calls")
+        assert fused == (1 if (padlen is None or padlen >= 62) else 0), padlen
+        assert two.get_option("filtfilt_fused_calls") == 0
+        want = O.filtfilt_fir(b, x, code, -1 if padlen is None else padlen)
+        t = tol(hc, x, 3.0 * 2)
+        assert np.abs(y1.cpu().numpy() - want).max() <= t
+        assert np.abs(y2.cpu().numpy() - want).max() <= t
+
+
 def test_filtfilt_identity_and_errors():
     x = np.arange(12, dtype=np.float32)
     np.testing.assert_allclose(signal.filtfilt([1.0], [1.0], x), x, atol=1e-6)      # test_signaltools.py:2797-2804

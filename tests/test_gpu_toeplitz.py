@@ -115,9 +115,14 @@ def test_toeplitz_filtfilt_matches_direct_and_oracle(padtype, loader):
                                          None: O.PAD_NONE}[padtype])
     ctx = toep_ctx(4, loader)
     y = run(ctx, lambda: signal.filtfilt(b, [1.0], dev(x), padtype=padtype, ctx=ctx)).cpu().numpy()
-    assert ctx.get_option("toeplitz_launches") == 2
+    assert ctx.get_option("toeplitz_launches") == (2 if padtype is None else 1)    # padded filtfilt is one fused pass
+    two = toep_ctx(3, loader)
+    two.set_option("filtfilt_fused", 0)                              # the two-pass form (anticausal kernel path)
+    y2 = run(two, lambda: signal.filtfilt(b, [1.0], dev(x), padtype=padtype, ctx=two)).cpu().numpy()
+    assert two.get_option("toeplitz_launches") == 2
     hc = np.convolve(b.astype(np.float64), b[::-1].astype(np.float64))
     assert np.abs(y - want).max() <= tol(hc, x) * 2
+    assert np.abs(y2 - want).max() <= tol(hc, x) * 2
     yz = run(ctx, lambda: signal.filtfilt_zero_state(b, dev(x), ctx=ctx)).cpu().numpy()
     assert np.abs(yz - O.filtfilt_fir_nopad(b, x)).max() <= tol(hc, x) * 2
 
