@@ -84,6 +84,19 @@ static int check_matrix(const void* p, int64_t ld, int64_t batch, int64_t n, con
     return SCIR_B200_OK;
 }
 
+// The kernels read a tile plus its halo while other CTAs write their outputs: filtering in place is undefined.
+// (The reference always returns a fresh array, lib.rs:1044.)  Elementwise ops are the exception and say so.
+template <typename T>
+static int check_no_alias(const T* x, int64_t ld_x, int64_t nx, const T* y, int64_t ld_y, int64_t ny, int64_t batch)
+{
+    if (batch <= 0 || nx <= 0 || ny <= 0 || x == nullptr || y == nullptr) return SCIR_B200_OK;
+    const T* xe = x + (batch - 1) * ld_x + nx;
+    const T* ye = y + (batch - 1) * ld_y + ny;
+    if (x < ye && y < xe)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "x and y overlap: the FIR routes cannot run in place");
+    return SCIR_B200_OK;
+}
+
 static int check_taps(const float* taps, int64_t k)
 {
     if (taps == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "taps is NULL");
@@ -579,6 +592,7 @@ int scir_b200_fir1d_batched_f32(scir_b200_ctx* ctx, const float* d_x, int64_t ld
         return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n, d_y, ld_y, n, batch));
     std::vector<float> c;
     reorder_taps(taps, k, tap_order, c);
     return fir_causal(ctx, c.data(), k, d_x, ld_x, d_y, ld_y, batch, n);
@@ -611,6 +625,7 @@ int scir_b200_lfilter_fir_f32(scir_b200_ctx* ctx, const float* b, int64_t k, flo
     if (a0 == 0.f) return set_error(SCIR_B200_ERR_INVALID_ARG, "a[0] must be nonzero");
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n, d_y, ld_y, n, batch));
     std::vector<float> c(static_cast<size_t>(k));
     for (int64_t d = 0; d < k; ++d) c[static_cast<size_t>(d)] = b[d] / a0;     // _signaltools.py:2223
     SCIR_TRY(fir_causal(ctx, c.data(), k, d_x, ld_x, d_y, ld_y, batch, n));
@@ -637,6 +652,7 @@ int scir_b200_upfirdn_f32(scir_b200_ctx* ctx, const float* h, int64_t len_h, int
         return set_error(SCIR_B200_ERR_INVALID_ARG, "output window [%lld, %lld) outside the upfirdn result",
                          (long long)m_begin, (long long)(m_begin + m_count));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, m_count, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n_in, d_y, ld_y, m_count, batch));
     if (batch == 0 || m_count == 0) return SCIR_B200_OK;
     return launch_upfirdn(ctx, h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin, m_count);
 }
@@ -661,6 +677,7 @@ int scir_b200_resample_poly_f32(scir_b200_ctx* ctx, const float* window, int64_t
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n_in, "x"));
     const int64_t n_out = (pl.up == 1 && pl.down == 1) ? n_in : pl.n_out;
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n_out, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n_in, d_y, ld_y, n_out, batch));
     return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y);
 }
 
@@ -677,6 +694,7 @@ int scir_b200_upfirdn_mode_f32(scir_b200_ctx* ctx, const float* h, int64_t len_h
         return set_error(SCIR_B200_ERR_INVALID_ARG, "output window [%lld, %lld) outside the upfirdn result",
                          (long long)m_begin, (long long)(m_begin + m_count));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, m_count, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n_in, d_y, ld_y, m_count, batch));
     if (batch == 0 || m_count == 0) return SCIR_B200_OK;
     return launch_upfirdn(ctx, h, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, m_begin, m_count, mode, cval);
 }
@@ -693,6 +711,7 @@ int scir_b200_resample_poly_pad_f32(scir_b200_ctx* ctx, const float* window, int
     const bool copy = (pl.up == 1 && pl.down == 1);
     const int64_t n_out = copy ? n_in : pl.n_out;
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n_out, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n_in, d_y, ld_y, n_out, batch));
     if (padtype >= SCIR_B200_EXT_CONSTANT && padtype <= SCIR_B200_EXT_LINE)
         return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, padtype, cval);
     if (padtype == SCIR_B200_PAD_STAT_MEDIAN)
@@ -745,6 +764,7 @@ int scir_b200_filtfilt_fir_f32(scir_b200_ctx* ctx, const float* b, int64_t k, in
     SCIR_TRY(check_taps(b, k));
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n, d_y, ld_y, n, batch));
     return filtfilt_device(ctx, b, k, pad_mode, padlen, d_x, ld_x, d_y, ld_y, batch, n);
 }
 
@@ -773,6 +793,7 @@ int scir_b200_fir1d_batched_f64(scir_b200_ctx* ctx, const double* d_x, int64_t l
         return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
+    SCIR_TRY(check_no_alias(d_x, ld_x, n, d_y, ld_y, n, batch));
     std::vector<double> c(static_cast<size_t>(k));
     for (int64_t d = 0; d < k; ++d) c[static_cast<size_t>(d)] = (tap_order == SCIR_B200_TAPS_SCIR) ? taps[k - 1 - d] : taps[d];
     return launch_fir_f64(ctx, d_x, ld_x, c.data(), k, d_y, ld_y, batch, n);

@@ -202,7 +202,8 @@ __device__ __forceinline__ void poly_store_acc(float* so, const float (&acc)[R])
 // zero taps; NCH: compile-time chunk count (0 = runtime loop, taps through LDCU).
 template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
 __global__ void __launch_bounds__(kPolyNT, 3)
-upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps)
+upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps,
+                    const __grid_constant__ PolyPairs pairs, int packed)
 {
     constexpr int NT = kPolyNT;
     constexpr int R = UP * G;
@@ -248,7 +249,12 @@ upfirdn_tile_kernel(const __grid_constant__ PolyParams q, const __grid_constant_
     }
 
     float acc[R];
-    poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, smem + HALO + tid * SIN, nchunk, taps);
+    if constexpr (NCH == 1) {
+        if (packed) poly_core2<UP, DOWN, G, KCP, Z>(acc, smem + HALO + tid * SIN, taps, pairs);
+        else poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, smem + HALO + tid * SIN, nchunk, taps);
+    } else {
+        poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, smem + HALO + tid * SIN, nchunk, taps);
+    }
 
     __syncthreads();                                        // every warp is done reading the tile
     poly_store_acc<R>(smem + tid * R, acc);
@@ -394,7 +400,12 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
     const size_t len = static_cast<size_t>(halo) + kPolyNT * SIN + 4;
     const size_t stream_bytes = (2 * len + static_cast<size_t>(kPolyNT) * R) * sizeof(float);
     const int d = ctx->device & 15;
-    if (ctx->opt.upfirdn_variant != 3 && stream_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
+    thread_local PolyPairs* pairs = nullptr;
+    if (!pairs) pairs = new PolyPairs();
+    // upfirdn_variant: 0 auto (streaming, FFMA2) | 3 one tile per CTA (FFMA2) | 4 streaming, scalar FFMA | 5 tile, scalar FFMA
+    const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4 && ctx->opt.upfirdn_variant != 5) ? 1 : 0;
+    if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
+    if (ctx->opt.upfirdn_variant != 3 && ctx->opt.upfirdn_variant != 5 && stream_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
         // persistent grid: every SM holds as many CTAs as fit; each walks tiles with stride gridDim.x
         auto kern = upfirdn_stream_kernel<UP, DOWN, G, KCP, Z, NCH>;
         static thread_local size_t configured[16] = {0};
@@ -413,10 +424,6 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
             occ_smem[d] = stream_bytes;
         }
         const long long g = std::min<long long>(grid, static_cast<long long>(ctx->sm_count) * resident[d]);
-        thread_local PolyPairs* pairs = nullptr;
-        if (!pairs) pairs = new PolyPairs();
-        const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4) ? 1 : 0;   // upfirdn_variant=4: scalar-FFMA A/B arm
-        if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
         kern<<<static_cast<unsigned>(g), kPolyNT, stream_bytes, ctx->stream>>>(q, taps, batch, *pairs, packed);
         SCIR_CUDA(cudaGetLastError(), "upfirdn_stream_kernel launch");
         ctx->launches++;
@@ -434,7 +441,7 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
                   "cudaFuncSetAttribute(upfirdn_tile_kernel)");
         configured[d] = smem_bytes;
     }
-    kern<<<static_cast<unsigned>(grid), kPolyNT, smem_bytes, ctx->stream>>>(q, taps);
+    kern<<<static_cast<unsigned>(grid), kPolyNT, smem_bytes, ctx->stream>>>(q, taps, *pairs, packed);
     SCIR_CUDA(cudaGetLastError(), "upfirdn_tile_kernel launch");
     ctx->launches++;
     ctx->poly_launches++;

@@ -603,6 +603,22 @@ def test_filtfilt_single_pass_equals_two_pass(padtype):
         assert np.abs(y2.cpu().numpy() - want).max() <= t
 
 
+def test_in_place_filtering_is_rejected():
+    """x and y may not overlap (tiles read their halo while other CTAs store): INVALID_ARG, not silent garbage."""
+    lib = L.lib()
+    ctx = gpu.Context(0)
+    t = dev(np.ones((4, 1000), np.float32))
+    taps = np.ones(5, np.float32)
+    p = C.c_void_p(t.data_ptr())
+    rc = lib.scir_b200_fir1d_batched_f32(ctx.handle, p, 1000, taps.ctypes.data_as(C.c_void_p), 5, L.TAPS_SCIR, p, 1000, 4, 1000)
+    assert rc == L.ERR_INVALID_ARG and "in place" in L.last_error()
+    p2 = C.c_void_p(t.data_ptr() + 4 * 500)                            # partial overlap
+    rc = lib.scir_b200_fir1d_batched_f32(ctx.handle, p, 1000, taps.ctypes.data_as(C.c_void_p), 5, L.TAPS_SCIR, p2, 1000, 2, 1000)
+    assert rc == L.ERR_INVALID_ARG
+    rc = lib.scir_b200_filtfilt_fir_f32(ctx.handle, taps.ctypes.data_as(C.c_void_p), 5, L.PAD_ODD, -1, p, 1000, p, 1000, 4, 1000)
+    assert rc == L.ERR_INVALID_ARG
+
+
 def test_filtfilt_identity_and_errors():
     x = np.arange(12, dtype=np.float32)
     np.testing.assert_allclose(signal.filtfilt([1.0], [1.0], x), x, atol=1e-6)      # test_signaltools.py:2797-2804
