@@ -471,8 +471,7 @@ TRAFFIC_PER_LAUNCH = {
     "c2": 8.576e9,      # profiles/r01_c2_fir_toeplitz_kernel_final.ncu.txt: 4.314 GB read + 4.262 GB written (algorithmic 8.590e9)
     "c3": 8.543e9,      # profiles/r01_c3_fir_toeplitz_kernel_final.ncu.txt: 4.297 + 4.246           (algorithmic 8.590e9)
     "c4": 21.450e9,     # profiles/r01_c4_upfirdn_stream_kernel_ffma2.ncu.txt: 8.612 + 12.838        (algorithmic 21.475e9)
-    "c5": None,         # fused single-pass filtfilt not captured yet (two-pass form: 17.25e9 per pass,
-                        # profiles/r01_c5_fir_toeplitz_kernel_final.ncu.txt; algorithmic 17.18e9 per pass)
+    "c5": 17.169e9,     # profiles/r01_c5_fir_toeplitz_kernel_fused.ncu.txt (one fused pass): 8.599 + 8.570 (algorithmic 17.180e9)
 }
 
 if __name__ == "__main__":

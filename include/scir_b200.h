@@ -225,6 +225,16 @@ SCIR_B200_API int scir_b200_mg_fir1d_batched_f32_host(scir_b200_mg *mg,
                                         float *h_y, int64_t ld_y,
                                         int64_t batch, int64_t n);
 
+SCIR_B200_API int scir_b200_mg_resample_poly_f32_host(scir_b200_mg *mg,
+                                        const float *window, int64_t len_h, int64_t up, int64_t down,
+                                        const float *h_x, int64_t ld_x, int64_t batch, int64_t n_in,
+                                        float *h_y, int64_t ld_y);
+SCIR_B200_API int scir_b200_mg_filtfilt_fir_f32_host(scir_b200_mg *mg,
+                                       const float *b, int64_t k, int pad_mode, int64_t padlen,
+                                       const float *h_x, int64_t ld_x,
+                                       float *h_y, int64_t ld_y,
+                                       int64_t batch, int64_t n);
+
 /* ---- measurement helpers (bench.py): what the SAME box sustains, as roofline denominators ----- */
 SCIR_B200_API int scir_b200_microbench_ffma(scir_b200_ctx *ctx, int iters, double *tflops);      /* FP32 FFMA peak   */
 SCIR_B200_API int scir_b200_microbench_ffma2(scir_b200_ctx *ctx, int iters, int mix, double *tflops); /* packed FFMA2 (+mix) */

@@ -72,6 +72,8 @@ SIGNATURES = {
     "scir_b200_mg_device_count": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "scir_b200_shard_rows": (C.c_int, [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]),
     "scir_b200_mg_fir1d_batched_f32_host": (C.c_int, [vp, fp, i64, fp, i64, C.c_int, fp, i64, i64, i64]),
+    "scir_b200_mg_resample_poly_f32_host": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64]),
+    "scir_b200_mg_filtfilt_fir_f32_host": (C.c_int, [vp, fp, i64, C.c_int, i64, fp, i64, fp, i64, i64, i64]),
     "scir_b200_microbench_ffma": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
     "scir_b200_microbench_ffma2": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "scir_b200_microbench_copy": (C.c_int, [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),

@@ -738,15 +738,16 @@ def test_elementwise_unaligned_views_and_aliasing():
 
 
 def test_mg_row_sharding_matches_single_device():
+    """In-process multi-GPU front end (one ctx + host thread per shard, no collective).  On a one-GPU box the
+    same device is listed three times: the sharding, threading and error plumbing are identical."""
     ndev = gpu.device_count()
-    if ndev < 2:
-        pytest.skip("needs >= 2 GPUs")
+    ids = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
     lib = L.lib()
-    devs = (C.c_int * ndev)(*range(ndev))
+    devs = (C.c_int * len(ids))(*ids)
     mg = C.c_void_p()
-    assert lib.scir_b200_mg_create(devs, ndev, C.byref(mg)) == 0, L.last_error()
+    assert lib.scir_b200_mg_create(devs, len(ids), C.byref(mg)) == 0, L.last_error()
     rng = np.random.RandomState(8)
-    x = (rng.rand(4 * ndev + 1, 30000).astype(np.float32) * 2 - 1)
+    x = (rng.rand(4 * len(ids) + 1, 30000).astype(np.float32) * 2 - 1)      # uneven shards
     taps = rng.randn(63).astype(np.float32)
     y = np.empty_like(x)
     rc = lib.scir_b200_mg_fir1d_batched_f32_host(mg, x.ctypes.data, x.shape[1], taps.ctypes.data, taps.size, 0,
@@ -754,4 +755,23 @@ def test_mg_row_sharding_matches_single_device():
     assert rc == 0, L.last_error()
     assert np.array_equal(y, gpu.fir1d_batched_f32_cuda(x, taps))
     assert np.abs(y - O.fir1d_batched_f32_acc64(x, taps)).max() <= tol(taps, x)
+    # resample_poly and filtfilt through the same front end
+    from scipy.signal import firwin
+    h = firwin(96, 1.0 / 3.0, window=("kaiser", 5.0)).astype(np.float32)
+    n_out = -(-x.shape[1] * 3 // 2)
+    yr = np.empty((x.shape[0], n_out), np.float32)
+    rc = lib.scir_b200_mg_resample_poly_f32_host(mg, h.ctypes.data, h.size, 3, 2, x.ctypes.data, x.shape[1], x.shape[0],
+                                                 x.shape[1], yr.ctypes.data, n_out)
+    assert rc == 0, L.last_error()
+    assert np.array_equal(yr, signal.resample_poly(x, 3, 2, h))
+    b = firwin(31, 0.2).astype(np.float32)
+    yf = np.empty_like(x)
+    rc = lib.scir_b200_mg_filtfilt_fir_f32_host(mg, b.ctypes.data, b.size, L.PAD_ODD, -1, x.ctypes.data, x.shape[1],
+                                                yf.ctypes.data, x.shape[1], x.shape[0], x.shape[1])
+    assert rc == 0, L.last_error()
+    assert np.array_equal(yf, signal.filtfilt(b, [1.0], x))
+    # a failing shard reports which one
+    rc = lib.scir_b200_mg_filtfilt_fir_f32_host(mg, b.ctypes.data, b.size, L.PAD_ODD, 10 ** 6, x.ctypes.data, x.shape[1],
+                                                yf.ctypes.data, x.shape[1], x.shape[0], x.shape[1])
+    assert rc == L.ERR_SHAPE and "shard" in L.last_error()
     lib.scir_b200_mg_destroy(mg)
