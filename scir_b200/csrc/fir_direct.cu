@@ -370,7 +370,7 @@ fir_stream_kernel(const __grid_constant__ FirTileParams q, const __grid_constant
         }
 
         float acc[R];
-        fir_core_any<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.nchunk, taps, q.packed);
+        fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.nchunk, taps);   // scalar A/B arm
 
         if (tid == 0) bulk_store_wait_read<0>();           // the previous tile's store has drained `out`
         if (any_nonfinite<R>(acc)) exact_redo<R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + tid * R) : (in + tid * R), q.k, taps);
@@ -397,118 +397,7 @@ fir_stream_kernel(const __grid_constant__ FirTileParams q, const __grid_constant
     if (tid == 0) bulk_store_wait_read<0>();               // smem must outlive the last store's read
 }
 
-// ---- the warp-streaming kernel (default for K <= 256) ---------------------------------------------------
-// No CTA-wide barrier anywhere: every WARP is its own pipeline.  A warp owns two input stages and one
-// output buffer in shared memory, walks warp-tiles (32*R outputs) of the (row, tile) grid with stride
-// "all warps of the grid", prefetches two tiles ahead with cp.async.bulk on its own mbarriers (lane 0
-// issues) and drains results with a bulk store.  Warps drift freely, so an SM sub-partition always
-// has a warp in its FFMA stream while others wait for data; the halo is re-read from L2 per warp
-// (K-1 of 32*R+K-1 samples), which is why long filters use the CTA-tile kernel instead.
-struct WarpTileParams {
-    FirPass p;
-    long long base0;          // virtual index of the first output of tile 0
-    int ntiles;               // warp-tiles per row
-    int nchunk;
-    int in_lo, in_cnt;        // tiles [in_lo, in_lo+in_cnt) may be bulk-loaded (fully inside the row, aligned)
-    int out_lo, out_cnt;      // tiles [out_lo, out_lo+out_cnt) may be bulk-stored
-};
-
-template <int KC, int R, int DIR, int MAXK, int NW>
-__global__ void __launch_bounds__(NW * 32, (NW == 1) ? 20 : 5)
-fir_warp_kernel(const __grid_constant__ WarpTileParams q, const __grid_constant__ TapsParam<MAXK> taps)
-{
-    static_assert(KC % 4 == 0 && R % 4 == 0 && (R / 4) % 2 == 1, "conflict-free LDS.128 on a dense tile");
-    constexpr int WT = 32 * R;
-    extern __shared__ __align__(128) float smem[];     // per warp: in[0] | in[1] | out
-    __shared__ __align__(8) unsigned long long full[NW][2];
-
-    const FirPass& p = q.p;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int DP = q.nchunk * KC;
-    const int len = DP + WT;
-    float* const mine = smem + warp * (2 * len + WT);
-    float* const out_s = mine + 2 * len;
-    const uint32_t bar0 = smem_u32(&full[warp][0]);
-    const int GW = gridDim.x * NW;                         // warps in the grid
-    const int step_row = GW / q.ntiles, step_tile = GW - step_row * q.ntiles;
-
-    int row = (blockIdx.x * NW + warp) / q.ntiles;
-    int tile = (blockIdx.x * NW + warp) - row * q.ntiles;
-    int nrow = row, ntile = tile;                          // runs two tiles ahead
-    auto advance = [&](int& r, int& t) {
-        r += step_row;
-        t += step_tile;
-        if (t >= q.ntiles) {
-            t -= q.ntiles;
-            r += 1;
-        }
-    };
-    auto prefetch = [&](int r, int t, int s) {             // lane 0 only
-        if (r >= p.batch || static_cast<unsigned>(t - q.in_lo) >= static_cast<unsigned>(q.in_cnt)) return;
-        const long long i0 = q.base0 + static_cast<long long>(t) * WT;
-        const long long a = (DIR > 0) ? (i0 - DP) : i0;
-        mbar_arrive_expect_tx(bar0 + 8u * s, static_cast<uint32_t>(len) * 4u);
-        bulk_copy_g2s(smem_u32(mine + s * len), p.x + r * p.ld_x + a + p.in_off, static_cast<uint32_t>(len) * 4u,
-                      bar0 + 8u * s);
-    };
-
-    if (lane == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8u, 1);
-        fence_mbar_init();
-        prefetch(nrow, ntile, 0);
-    }
-    advance(nrow, ntile);
-    if (lane == 0) prefetch(nrow, ntile, 1);
-    advance(nrow, ntile);
-    __syncwarp();
-
-    uint32_t phases = 0;                                   // bit s = parity to wait for on full[s]
-    for (int it = 0; row < p.batch; ++it) {
-        const int s = it & 1;
-        const long long i0 = q.base0 + static_cast<long long>(tile) * WT;
-        float* const in = mine + s * len;
-
-        if (static_cast<unsigned>(tile - q.in_lo) < static_cast<unsigned>(q.in_cnt)) {
-            mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
-            phases ^= 1u << s;
-        } else {                                           // edge tile: zero / held / extended samples
-            const long long a = (DIR > 0) ? (i0 - DP) : i0;
-            const float* __restrict__ xr = p.x + row * p.ld_x;
-            for (int t = lane; t < len; t += 32) in[t] = vload(p, xr, a + t);
-            __syncwarp();
-        }
-
-        float acc[R];
-        fir_core<KC, R, DIR, MAXK>(acc, (DIR > 0) ? (in + DP + lane * R) : (in + lane * R), q.nchunk, taps);
-
-        if (lane == 0) bulk_store_wait_read<0>();          // the previous tile's store has drained `out`
-        __syncwarp();                                      // in[s] consumed by every lane, out free
-        if (lane == 0) prefetch(nrow, ntile, s);           // refill in[s] two tiles ahead
-
-        float4* so = reinterpret_cast<float4*>(out_s + lane * R);
-#pragma unroll
-        for (int r = 0; r < R; r += 4) so[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
-
-        float* __restrict__ yr = p.y + row * p.ld_y;
-        if (static_cast<unsigned>(tile - q.out_lo) < static_cast<unsigned>(q.out_cnt)) {
-            fence_proxy_async_smem();                      // generic-proxy writes -> async proxy
-            __syncwarp();
-            if (lane == 0) bulk_copy_s2g(yr + i0 + p.out_off, smem_u32(out_s), WT * 4u);
-        } else {
-            __syncwarp();
-            for (int t = lane; t < WT; t += 32) {
-                const long long i = i0 + t;
-                if (i >= p.out_begin && i < p.out_end) yr[i + p.out_off] = out_s[t];
-            }
-            __syncwarp();                                  // out is rewritten by the next tile's STS
-        }
-        advance(row, tile);
-        advance(nrow, ntile);
-    }
-    if (lane == 0) bulk_store_wait_read<0>();              // smem must outlive the last store's read
-}
-
+#ifndef SCIR_FIR_DIRECT_REV   // the direction-independent pieces live in the forward translation unit only
 // ---- naive kernel: one thread per output, taps from global memory ------------------------------------
 // An independent implementation of the same FirPass (what the reference's PTX entry was meant to
 // do, lib.rs:744-809).  Kept for A/B profiling (`variant=2`) and as a cross-check in the tests.
@@ -557,6 +446,8 @@ __global__ void compute_zf_kernel(const float* __restrict__ b, int k, const floa
     zf[row * km1 + j] = acc;
 }
 
+#endif  // !SCIR_FIR_DIRECT_REV
+
 // ---- host side ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -579,7 +470,7 @@ int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int6
     // One tile per CTA (4 CTAs/SM overlap each other's copies) is the default: with the packed FFMA2 core it beats the
     // persistent CTA-streaming kernel at every size (profiles/r01_dispatch_sweep.txt: 10-20 % for K <= 128), whose
     // two CTA barriers per tile are no longer hidden behind FFMA issue.  Streaming stays as the scalar-core default
-    // for short filters (ffma2=0) and as variant 4.
+    // for short filters (ffma2=0) and as variant 4; it carries the scalar core only.
     const bool packed = (MAXK <= kPackedMaxK && ctx->opt.ffma2 != 0);
     const bool stream = (ctx->opt.variant == 4) || (ctx->opt.variant != 3 && q.nchunk <= 2 && !packed);
     const size_t smem_bytes = (stream ? (2 * len + kTile) : len) * sizeof(float);
@@ -619,78 +510,25 @@ int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int6
     return SCIR_B200_OK;
 }
 
-template <int KC, int R, int DIR, int MAXK>
-int launch_warp(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k, bool generic_io)
-{
-    constexpr int NW = 1, WT = 32 * R;                     // one warp per CTA: everything is CTA-uniform => UR-form FFMA
-    thread_local TapsParam<MAXK>* tl = nullptr;
-    if (!tl) tl = new TapsParam<MAXK>();
-    for (int i = 0; i < MAXK; ++i) tl->c[i] = (i < k) ? c[i] : 0.f;
-
-    WarpTileParams q{};
-    q.p = pass;
-    q.nchunk = static_cast<int>((k + KC - 1) / KC);
-    const long long DP = static_cast<long long>(q.nchunk) * KC, len = DP + WT;
-    const long long mis = (((pass.out_begin + pass.in_off) % 4) + 4) % 4;
-    q.base0 = pass.out_begin - mis;                        // input address of tile 0 is 16-B aligned
-    const long long ntiles = (pass.out_end - q.base0 + WT - 1) / WT;
-    if (ntiles * pass.batch > 0x7fffffffLL || pass.batch > 0x7fffffffLL)
-        return set_error(SCIR_B200_ERR_UNSUPPORTED, "grid too large (%lld warp tiles)", ntiles * pass.batch);
-    q.ntiles = static_cast<int>(ntiles);
-    // interior tile ranges, in tile units (ceil/floor of the sample-index conditions)
-    auto ceil_div = [](long long a, long long b) { return (a >= 0) ? (a + b - 1) / b : -((-a) / b); };
-    auto floor_div = [](long long a, long long b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
-    const bool in_ok = !generic_io && aligned16(pass.x) && (pass.ld_x % 4 == 0);
-    const bool out_ok = !generic_io && aligned16(pass.y) && (pass.ld_y % 4 == 0) &&
-                        ((((q.base0 + pass.out_off) % 4) + 4) % 4 == 0);
-    {   // first staged sample a(t) = base0 + t*WT - (DIR>0 ? DP : 0); need a >= lo_v and a + len <= hi_v
-        long long lo_v = 0, hi_v = pass.n_v;
-        if (pass.ext_mode != EXT_NONE) {
-            lo_v = std::max<long long>(lo_v, -pass.in_off);
-            hi_v = std::min<long long>(hi_v, pass.n_x - pass.in_off);
-        }
-        const long long off = q.base0 - ((DIR > 0) ? DP : 0);
-        const long long t_lo = std::max<long long>(0, ceil_div(lo_v - off, WT));
-        const long long t_hi = std::min<long long>(ntiles - 1, floor_div(hi_v - len - off, WT));
-        q.in_lo = static_cast<int>(t_lo);
-        q.in_cnt = (in_ok && t_hi >= t_lo) ? static_cast<int>(t_hi - t_lo + 1) : 0;
-    }
-    {   // i0(t) = base0 + t*WT >= out_begin and i0 + WT <= out_end
-        const long long t_lo = std::max<long long>(0, ceil_div(pass.out_begin - q.base0, WT));
-        const long long t_hi = std::min<long long>(ntiles - 1, floor_div(pass.out_end - WT - q.base0, WT));
-        q.out_lo = static_cast<int>(t_lo);
-        q.out_cnt = (out_ok && t_hi >= t_lo) ? static_cast<int>(t_hi - t_lo + 1) : 0;
-    }
-
-    const size_t smem_bytes = static_cast<size_t>(NW) * (2 * len + WT) * sizeof(float);
-    if (smem_bytes > static_cast<size_t>(ctx->max_smem_optin))
-        return set_error(SCIR_B200_ERR_UNSUPPORTED, "warp tiles need %zu B of shared memory", smem_bytes);
-    auto kern = fir_warp_kernel<KC, R, DIR, MAXK, NW>;
-    static thread_local size_t configured[16] = {};
-    static thread_local size_t occ_smem[16] = {};
-    static thread_local int resident[16] = {};
-    const int d = ctx->device & 15;
-    if (configured[d] < smem_bytes) {
-        SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)),
-                  "cudaFuncSetAttribute(fir_warp_kernel)");
-        configured[d] = smem_bytes;
-    }
-    if (resident[d] == 0 || occ_smem[d] != smem_bytes) {
-        int nb = 0;
-        SCIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NW * 32, smem_bytes),
-                  "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-        resident[d] = std::max(nb, 1);
-        occ_smem[d] = smem_bytes;
-    }
-    const long long total_warps = ntiles * pass.batch;
-    const long long grid = std::min<long long>((total_warps + NW - 1) / NW, static_cast<long long>(ctx->sm_count) * resident[d]);
-    kern<<<static_cast<unsigned>(grid), NW * 32, smem_bytes, ctx->stream>>>(q, *tl);
-    SCIR_CUDA(cudaGetLastError(), "fir_warp_kernel launch");
-    ctx->launches++;
-    return SCIR_B200_OK;
-}
-
 }  // namespace
+
+// The causal and the anticausal instantiations compile in separate translation units (fir_direct_rev.cu includes
+// this file with SCIR_FIR_DIRECT_REV defined): the fully unrolled cores make this the slowest file to build.
+#ifdef SCIR_FIR_DIRECT_REV
+int launch_fir_tiles_rev(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int64_t k, long long grid, int kc, bool small)
+{
+    if (kc == 32) return launch_tile<32, -1, kSmallK>(ctx, q, c, k, grid);
+    if (small) return launch_tile<64, -1, kSmallK>(ctx, q, c, k, grid);
+    return launch_tile<64, -1, kBigK>(ctx, q, c, k, grid);
+}
+#else
+int launch_fir_tiles_rev(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int64_t k, long long grid, int kc, bool small);
+static int launch_fir_tiles_fwd(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int64_t k, long long grid, int kc, bool small)
+{
+    if (kc == 32) return launch_tile<32, +1, kSmallK>(ctx, q, c, k, grid);
+    if (small) return launch_tile<64, +1, kSmallK>(ctx, q, c, k, grid);
+    return launch_tile<64, +1, kBigK>(ctx, q, c, k, grid);
+}
 
 int launch_fir_pass(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
 {
@@ -716,25 +554,7 @@ int launch_fir_pass(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int
         return SCIR_B200_OK;
     }
 
-    // variant: 0 auto | 1 generic (non-bulk) IO | 2 naive | 3 one-tile-per-CTA | 4 CTA-streaming |
-    //          5 warp-streaming R=20 | 6 warp-streaming R=28
-    const int64_t v = ctx->opt.variant;
-    const bool warp_path = (v == 5 || v == 6);
-    if (warp_path) {
-        const bool gio = false;
-        const bool r20 = (v == 5);
-        if (pass.dir > 0) {
-            if (k <= 32) return launch_warp<32, 28, +1, kSmallK>(ctx, pass, c, k, gio);
-            if (k > kSmallK) return launch_warp<64, 28, +1, kBigK>(ctx, pass, c, k, gio);
-            return r20 ? launch_warp<64, 20, +1, kSmallK>(ctx, pass, c, k, gio)
-                       : launch_warp<64, 28, +1, kSmallK>(ctx, pass, c, k, gio);
-        } else {
-            if (k <= 32) return launch_warp<32, 28, -1, kSmallK>(ctx, pass, c, k, gio);
-            if (k > kSmallK) return launch_warp<64, 28, -1, kBigK>(ctx, pass, c, k, gio);
-            return launch_warp<64, 28, -1, kSmallK>(ctx, pass, c, k, gio);
-        }
-    }
-
+    // variant: 0 auto | 1 generic (non-bulk) IO | 2 naive | 3 one-tile-per-CTA | 4 CTA-streaming
     FirTileParams q;
     q.p = pass;
     const int KC = (k <= 32) ? 32 : 64;
@@ -752,15 +572,7 @@ int launch_fir_pass(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int
     if (grid > 0x7fffffffLL) return set_error(SCIR_B200_ERR_UNSUPPORTED, "grid too large (%lld tiles)", grid);
 
     const bool small = (DP <= kSmallK);
-    if (pass.dir > 0) {
-        if (KC == 32) return launch_tile<32, +1, kSmallK>(ctx, q, c, k, grid);
-        if (small) return launch_tile<64, +1, kSmallK>(ctx, q, c, k, grid);
-        return launch_tile<64, +1, kBigK>(ctx, q, c, k, grid);
-    } else {
-        if (KC == 32) return launch_tile<32, -1, kSmallK>(ctx, q, c, k, grid);
-        if (small) return launch_tile<64, -1, kSmallK>(ctx, q, c, k, grid);
-        return launch_tile<64, -1, kBigK>(ctx, q, c, k, grid);
-    }
+    return (pass.dir > 0) ? launch_fir_tiles_fwd(ctx, q, c, k, grid, KC, small) : launch_fir_tiles_rev(ctx, q, c, k, grid, KC, small);
 }
 
 int launch_add_zi(scir_b200_ctx* ctx, float* d_y, int64_t ld_y, const float* d_zi, int64_t batch,
@@ -794,5 +606,7 @@ int launch_compute_zf(scir_b200_ctx* ctx, const float* b, int64_t k, const float
     SCIR_CUDA(cudaFreeAsync(d_b, ctx->stream), "cudaFreeAsync(b)");
     return SCIR_B200_OK;
 }
+
+#endif  // SCIR_FIR_DIRECT_REV
 
 }  // namespace scir_b200

@@ -136,8 +136,8 @@ def test_unaligned_and_strided_device_views():
     assert np.abs(out.cpu().numpy() - O.fir1d_batched_f32_acc64(big, taps)).max() <= tol(taps, big)
 
 
-@pytest.mark.parametrize("k,variant", [(31, 0), (63, 0), (255, 0), (700, 0), (63, 4), (255, 4), (63, 5), (255, 6),
-                                       (700, 6), (31, 3)])
+@pytest.mark.parametrize("k,variant", [(31, 0), (63, 0), (255, 0), (700, 0), (63, 4), (255, 4),
+                                       (700, 3), (31, 3)])
 def test_stream_kernel_many_tiles_per_cta(k, variant):
     """More tiles than resident CTAs (148 SMs x 3): every persistent CTA walks several tiles, both
     pipeline stages wrap, edge tiles (non-bulk) interleave with bulk tiles.  Checked against the
@@ -167,7 +167,7 @@ def test_stream_kernel_many_tiles_per_cta(k, variant):
     assert torch.equal(y, y3)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_kernel_variants_agree(variant):
     """variant 1 = generic (non-bulk) IO, 2 = naive 1-thread/output kernel, 3 = one-tile-per-CTA kernel,
     4 = CTA-streaming kernel, 5/6 = warp-streaming kernel with 20/28 outputs per thread."""
