@@ -170,6 +170,32 @@ public:
             release();
         }
     }
+    // Elementwise ops with device dispatch (lib.rs:268-377): the Device::Cuda arms, on the resident pointers.
+    // Bit-identical to the CPU loops lib.rs:206-255, so `_auto` gives the same values on either device.
+    DeviceArray add_scalar_auto(float alpha) const
+    {
+        DeviceArray out = like("add_scalar_auto");
+        check(scir_b200_add_scalar_f32(default_context().get(), static_cast<const float*>(dptr_), alpha,
+                                       static_cast<float*>(out.dptr_), static_cast<int64_t>(len())));
+        return out;
+    }
+    DeviceArray mul_scalar_auto(float alpha) const
+    {
+        DeviceArray out = like("mul_scalar_auto");
+        check(scir_b200_mul_scalar_f32(default_context().get(), static_cast<const float*>(dptr_), alpha,
+                                       static_cast<float*>(out.dptr_), static_cast<int64_t>(len())));
+        return out;
+    }
+    DeviceArray add_auto(const DeviceArray& other) const
+    {
+        if (shape_ != other.shape_) throw GpuError(GpuError::Kind::ShapeMismatch, "add_auto: shapes differ", SCIR_B200_ERR_SHAPE);   // lib.rs:304-306
+        if (other.device_ != Device::Cuda)
+            throw GpuError(GpuError::Kind::BackendUnavailable, "add_auto: both arrays must be on Device::Cuda", SCIR_B200_ERR_NO_DEVICE);
+        DeviceArray out = like("add_auto");
+        check(scir_b200_add_f32(default_context().get(), static_cast<const float*>(dptr_), static_cast<const float*>(other.dptr_),
+                                static_cast<float*>(out.dptr_), static_cast<int64_t>(len())));
+        return out;
+    }
     // Device-resident FIR: no PCIe traffic when chaining.
     DeviceArray fir1d_batched(const std::vector<float>& taps, int tap_order = SCIR_B200_TAPS_SCIR) const
     {
@@ -186,6 +212,19 @@ public:
     }
 
 private:
+    DeviceArray like(const char* what) const               // same shape, fresh device storage
+    {
+        if (device_ != Device::Cuda)
+            throw GpuError(GpuError::Kind::BackendUnavailable,
+                           std::string(what) + ": Device::Cpu arrays are served by the reference crate's CPU loops (lib.rs:206-255)",
+                           SCIR_B200_ERR_NO_DEVICE);
+        DeviceArray out;
+        out.shape_ = shape_; out.dtype_ = dtype_;
+        void* p = nullptr;
+        check(scir_b200_malloc(default_context().get(), std::max<std::size_t>(len(), 1) * sizeof(float), &p));
+        out.dptr_ = p; out.device_ = Device::Cuda;
+        return out;
+    }
     void release()
     {
         if (dptr_) scir_b200_free(default_context().get(), dptr_);

@@ -84,6 +84,23 @@ int main(int argc, char** argv)
         gpu::DeviceArray e = d.fir1d_batched(taps);
         const auto back = e.to_cpu_vec();
         for (int i = 0; i < 8; ++i) EXPECT(std::fabs(back[i] - want[i]) <= 1e-7f);
+        // elementwise _auto ops: the reference's doc-test vectors (lib.rs:258-262, :293-298, :345-350), chained on the device
+        gpu::DeviceArray da = gpu::DeviceArray::from_cpu_slice({3}, gpu::DType::F32, {1.0f, 2.0f, 3.0f});
+        gpu::DeviceArray db = gpu::DeviceArray::from_cpu_slice({3}, gpu::DType::F32, {0.5f, 1.5f, 2.5f});
+        bool cpu_threw = false;
+        try { (void)da.add_scalar_auto(1.0f); } catch (const gpu::GpuError&) { cpu_threw = true; }
+        EXPECT(cpu_threw);                                      // no CPU path in this backend
+        da.to_device(gpu::Device::Cuda);
+        db.to_device(gpu::Device::Cuda);
+        EXPECT(da.add_scalar_auto(1.0f).to_cpu_vec() == (std::vector<float>{2.0f, 3.0f, 4.0f}));
+        EXPECT(da.mul_scalar_auto(2.0f).to_cpu_vec() == (std::vector<float>{2.0f, 4.0f, 6.0f}));
+        EXPECT(da.add_auto(db).to_cpu_vec() == (std::vector<float>{1.5f, 3.5f, 5.5f}));
+        EXPECT(da.mul_scalar_auto(2.0f).add_scalar_auto(-1.0f).add_auto(db).to_cpu_vec() == (std::vector<float>{1.5f, 4.5f, 7.5f}));
+        gpu::DeviceArray dc = gpu::DeviceArray::from_cpu_slice({2}, gpu::DType::F32, {1.0f, 2.0f});
+        dc.to_device(gpu::Device::Cuda);
+        bool shape_threw = false;
+        try { (void)da.add_auto(dc); } catch (const gpu::GpuError& e) { shape_threw = (e.kind() == gpu::GpuError::Kind::ShapeMismatch); }
+        EXPECT(shape_threw);
     }
     std::printf("%s: %d failure(s)\n", mode.c_str(), fails);
     return fails ? 1 : 0;
