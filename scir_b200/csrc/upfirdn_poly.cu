@@ -392,6 +392,115 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
     if (tid == 0) bulk_store_wait_read<0>();               // smem must outlive the last store's read
 }
 
+// ---- the warp-pipelined kernel (A/B: upfirdn_variant = 6) -------------------------------------------------
+// No CTA barrier anywhere: every WARP owns two input stages and one output buffer, walks warp-tiles (32*R outputs)
+// with stride "all warps of the grid", prefetches two tiles ahead with cp.async.bulk on its own mbarriers and
+// drains results with a bulk store.  With the packed core arithmetic takes half the issue slots, so what the
+// streaming kernel still loses is its two CTA barriers per tile; here warps drift freely.  Single-chunk filters only.
+constexpr int kPolyWarps = 8;
+
+template <int UP, int DOWN, int G, int KCP, int Z>
+__global__ void __launch_bounds__(kPolyWarps * 32, 3)
+upfirdn_warp_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps, long long batch,
+                    const __grid_constant__ PolyPairs pairs, long long wtiles)
+{
+    constexpr int R = UP * G;
+    constexpr int SIN = DOWN * G;
+    constexpr int ZP = (Z > 0) ? 4 : 0;
+    constexpr int HALO = KCP + ZP;
+    constexpr int WT_OUT = 32 * R;
+    constexpr int WT_IN = 32 * SIN;
+    constexpr int LEN = HALO + WT_IN + 4;
+    static_assert(LEN % 4 == 0 && WT_OUT % 4 == 0 && (WT_OUT % (4 * UP)) == 0, "16-byte bulk copies and aligned q0");
+
+    extern __shared__ __align__(128) float smem[];     // per warp: in[0] | in[1] | out
+    __shared__ __align__(8) unsigned long long full[kPolyWarps][2];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* const mine = smem + warp * (2 * LEN + WT_OUT);
+    float* const out_s = mine + 2 * LEN;
+    const uint32_t bar0 = smem_u32(&full[warp][0]);
+    const long long GW = static_cast<long long>(gridDim.x) * kPolyWarps;
+    const long long step_row = GW / wtiles, step_tile = GW - step_row * wtiles;
+
+    const long long gw = static_cast<long long>(blockIdx.x) * kPolyWarps + warp;
+    long long row = gw / wtiles, tile = gw - row * wtiles;
+    long long nrow = row, ntile = tile;                    // runs two tiles ahead
+    auto advance = [&](long long& r, long long& t) {
+        r += step_row;
+        t += step_tile;
+        if (t >= wtiles) {
+            t -= wtiles;
+            r += 1;
+        }
+    };
+    auto first_sample = [&](long long t) {
+        const long long m0 = q.base_m + t * WT_OUT;
+        return (m0 / UP) * DOWN - HALO;
+    };
+    auto can_bulk = [&](long long a) { return q.in_vec_ok && a >= 0 && a + LEN <= q.n_in; };
+    auto prefetch = [&](long long r, long long t, int s) { // lane 0 only
+        if (r >= batch) return;
+        const long long a = first_sample(t);
+        if (!can_bulk(a)) return;
+        mbar_arrive_expect_tx(bar0 + 8u * s, LEN * 4u);
+        bulk_copy_g2s(smem_u32(mine + s * LEN), q.x + r * q.ld_x + a, LEN * 4u, bar0 + 8u * s);
+    };
+
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_mbar_init();
+        prefetch(nrow, ntile, 0);
+    }
+    advance(nrow, ntile);
+    if (lane == 0) prefetch(nrow, ntile, 1);
+    advance(nrow, ntile);
+    __syncwarp();
+
+    uint32_t phases = 0;
+    for (int it = 0; row < batch; ++it) {
+        const int s = it & 1;
+        const long long m0 = q.base_m + tile * WT_OUT;
+        const long long a = first_sample(tile);
+        float* const in = mine + s * LEN;
+        if (can_bulk(a)) {
+            mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
+            phases ^= 1u << s;
+        } else {                                           // edge tile: samples outside the row by extension mode
+            const float* __restrict__ xr = q.x + row * q.ld_x;
+            for (int t = lane; t < LEN; t += 32) in[t] = upfirdn_sample(xr, a + t, q.n_in, q.ext);
+            __syncwarp();
+        }
+
+        float acc[R];
+        poly_core2<UP, DOWN, G, KCP, Z>(acc, in + HALO + lane * SIN, taps, pairs);
+
+        if (lane == 0) bulk_store_wait_read<0>();          // the previous tile's store has drained `out`
+        __syncwarp();                                      // in[s] consumed by every lane, out free
+        if (lane == 0) prefetch(nrow, ntile, s);           // refill in[s] two tiles ahead
+
+        poly_store_acc<R>(out_s + lane * R, acc);
+
+        float* __restrict__ yr = q.y + row * q.ld_y;
+        if (q.out_vec_ok && m0 >= q.m_begin && m0 + WT_OUT <= q.m_end) {
+            fence_proxy_async_smem();                      // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) bulk_copy_s2g(yr + (m0 - q.m_begin), smem_u32(out_s), WT_OUT * 4u);
+        } else {
+            __syncwarp();
+            for (int t = lane; t < WT_OUT; t += 32) {
+                const long long m = m0 + t;
+                if (m >= q.m_begin && m < q.m_end) yr[m - q.m_begin] = out_s[t];
+            }
+            __syncwarp();                                  // out is rewritten by the next tile's stores
+        }
+        advance(row, tile);
+        advance(nrow, ntile);
+    }
+    if (lane == 0) bulk_store_wait_read<0>();              // smem must outlive the last store's read
+}
+
 template <int UP, int DOWN, int G, int KCP, int Z, int NCH>
 int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, int nchunk, long long grid, long long batch)
 {
@@ -403,8 +512,35 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
     thread_local PolyPairs* pairs = nullptr;
     if (!pairs) pairs = new PolyPairs();
     // upfirdn_variant: 0 auto (streaming, FFMA2) | 3 one tile per CTA (FFMA2) | 4 streaming, scalar FFMA | 5 tile, scalar FFMA
-    const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4 && ctx->opt.upfirdn_variant != 5) ? 1 : 0;
+    const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4 && ctx->opt.upfirdn_variant != 5) ? 1 : 0;   // 6: warp-pipelined (FFMA2)
     if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
+    if constexpr (NCH == 1) {
+        if (ctx->opt.upfirdn_variant == 6) {               // warp-pipelined A/B arm
+            constexpr int LEN = KCP + ((Z > 0) ? 4 : 0) + 32 * SIN + 4, WT_OUT = 32 * R;
+            const size_t bytes = static_cast<size_t>(kPolyWarps) * (2 * LEN + WT_OUT) * sizeof(float);
+            auto kern = upfirdn_warp_kernel<UP, DOWN, G, KCP, Z>;
+            static thread_local size_t configured[16] = {0};
+            static thread_local int resident[16] = {0};
+            if (configured[d] < bytes) {
+                SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)),
+                          "cudaFuncSetAttribute(upfirdn_warp_kernel)");
+                configured[d] = bytes;
+                int nb = 0;
+                SCIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kPolyWarps * 32, bytes),
+                          "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+                resident[d] = std::max(nb, 1);
+            }
+            const long long wtiles = (q.m_end - q.base_m + WT_OUT - 1) / WT_OUT;
+            const long long total_w = wtiles * batch;
+            const long long g = std::min<long long>((total_w + kPolyWarps - 1) / kPolyWarps,
+                                                    static_cast<long long>(ctx->sm_count) * resident[d]);
+            kern<<<static_cast<unsigned>(g), kPolyWarps * 32, bytes, ctx->stream>>>(q, taps, batch, *pairs, wtiles);
+            SCIR_CUDA(cudaGetLastError(), "upfirdn_warp_kernel launch");
+            ctx->launches++;
+            ctx->poly_launches++;
+            return SCIR_B200_OK;
+        }
+    }
     if (ctx->opt.upfirdn_variant != 3 && ctx->opt.upfirdn_variant != 5 && stream_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
         // persistent grid: every SM holds as many CTAs as fit; each walks tiles with stride gridDim.x
         auto kern = upfirdn_stream_kernel<UP, DOWN, G, KCP, Z, NCH>;

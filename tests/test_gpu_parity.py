@@ -365,6 +365,26 @@ def test_upfirdn_tile_kernel_rates(up, down, lead, trail, len_h):
         assert np.abs(yv.cpu().numpy() - want).max() <= tol(h, x)
 
 
+@pytest.mark.parametrize("variant", [3, 4, 5, 6])
+@pytest.mark.parametrize("up,down,len_h", [(3, 2, 97), (2, 3, 61), (1, 2, 33), (4, 3, 40)])
+def test_upfirdn_kernel_variants_agree(variant, up, down, len_h):
+    """upfirdn_variant: 3 one tile per CTA (FFMA2), 4 streaming scalar FFMA, 5 tile scalar, 6 warp-pipelined (FFMA2):
+    A/B arms of the default streaming FFMA2 kernel; same results to rounding, all inside the oracle tolerance."""
+    rng = np.random.RandomState(variant * 10 + up)
+    h = rng.randn(len_h).astype(np.float32)
+    x = (rng.rand(5, 70001).astype(np.float32) * 2 - 1)
+    want = O.upfirdn(h, x, up, down)
+    ctx = gpu.Context(0)
+    ctx.set_option("upfirdn_variant", variant)
+    for view in (dev(x), dev(x)[:, 1:], dev(x)[::2, 3:60000]):
+        y = signal.upfirdn(h, view, up, down, ctx=ctx)
+        ctx.sync()
+        w = O.upfirdn(h, view.cpu().numpy(), up, down)
+        assert y.shape == w.shape
+        assert np.abs(y.cpu().numpy() - w).max() <= tol(h, x)
+    assert want.shape[0] == 5
+
+
 def test_upfirdn_tile_kernel_is_the_one_that_runs():
     """The templated rates must be served by ONE tile-kernel launch (not the generic fallback)."""
     rng = np.random.RandomState(1)
