@@ -1,3 +1,5 @@
+"""FP32 issue microbenchmarks on the GPU box: scalar FFMA vs packed FFMA2 (+ interleaved integer work).
+Usage: python tools/mb_ffma2.py   (profiles/README.md quotes the numbers)"""
 import ctypes as C, sys
 sys.path.insert(0, '.')
 from scir_b200 import _lib as L, gpu

@@ -1,3 +1,5 @@
+"""Times the f64 device twin (scir_b200_fir1d_batched_f64) at 256 x 2^20 for a few tap counts.
+Usage (GPU box): python tools/time_f64.py"""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
