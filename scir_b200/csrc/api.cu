@@ -421,6 +421,7 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
     if (ctx->toep_flags.ptr) cudaFree(ctx->toep_flags.ptr);
     if (ctx->row_bg.ptr) cudaFree(ctx->row_bg.ptr);
     if (ctx->toep_taps.ptr) cudaFree(ctx->toep_taps.ptr);
+    if (ctx->gen_taps.ptr) cudaFree(ctx->gen_taps.ptr);
     for (int i = 0; i < 3; ++i) {
         if (ctx->stage_in[i].ptr) cudaFree(ctx->stage_in[i].ptr);
         if (ctx->stage_out[i].ptr) cudaFree(ctx->stage_out[i].ptr);
@@ -498,6 +499,10 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
     }
     if (key && !strcmp(key, "fixup_launches")) {                   // read-only statistic
         *value = static_cast<int64_t>(ctx->fixup_launches);
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "gen_tiled_launches")) {                   // read-only statistic
+        *value = static_cast<int64_t>(ctx->gen_tiled_launches);
         return SCIR_B200_OK;
     }
     if (key && !strcmp(key, "filtfilt_fused_calls")) {                   // read-only statistic

@@ -71,6 +71,9 @@ struct scir_b200_ctx {
     scir_b200::DeviceBuffer toep_flags;    // per-tile non-finite flags of the last Toeplitz launch
     scir_b200::DeviceBuffer toep_taps;     // taps of the Toeplitz kernel (device copy) ...
     std::vector<float> toep_taps_host;     // ... and what it currently holds
+    scir_b200::DeviceBuffer gen_taps;      // phase-transposed taps of the any-rate tiled polyphase kernel ...
+    std::vector<float> gen_taps_host;      // ... and what the buffer currently holds
+    uint64_t gen_tiled_launches = 0;       // launches served by it
     scir_b200::DeviceBuffer row_bg;        // resample_poly padtype statistics: one float per row
     // *_host streaming pipeline resources (lazily created)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;

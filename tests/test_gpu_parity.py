@@ -385,6 +385,42 @@ def test_upfirdn_kernel_variants_agree(variant, up, down, len_h):
     assert want.shape[0] == 5
 
 
+@pytest.mark.parametrize("up,down,len_h,n", [(160, 147, 3201, 30000), (147, 160, 3201, 30011), (5, 4, 101, 50000), (7, 3, 141, 20000),
+                                            (2, 5, 101, 40000), (441, 320, 2001, 9000), (5, 1, 33, 7000), (1, 7, 50, 60000),
+                                            (11, 13, 7, 5000)])
+def test_upfirdn_any_rate_tiled_kernel(up, down, len_h, n):
+    """Rates outside the template grid run on the tiled any-rate kernel (phase-transposed taps + input span in
+    shared memory), not on the one-thread-per-output fallback; values against the oracle, with and without a mode,
+    and equal to the fallback kernel's to rounding."""
+    rng = np.random.RandomState(up * 7 + down)
+    h = rng.randn(len_h).astype(np.float32)
+    x = (rng.rand(3, n).astype(np.float32) * 2 - 1)
+    ctx = gpu.Context(0)
+    g0 = ctx.get_option("gen_tiled_launches")
+    y = signal.upfirdn(h, dev(x), up, down, ctx=ctx)
+    ctx.sync()
+    assert ctx.get_option("gen_tiled_launches") == g0 + 1
+    want = O.upfirdn(h, x, up, down)
+    assert y.shape == want.shape
+    assert np.abs(y.cpu().numpy() - want).max() <= tol(h, x)
+    ym = signal.upfirdn(h, dev(x), up, down, mode="reflect", ctx=ctx)
+    ctx.sync()                                             # the ctx owns its stream: torch's .cpu() does not wait on it
+    ym = ym.cpu().numpy()
+    wm = O.upfirdn_mode(h, x, up, down, "reflect")
+    assert np.abs(ym - wm).max() <= tol(h, x, 2.0)
+    old = gpu.Context(0)
+    old.set_option("upfirdn_variant", 1)                   # one thread per output
+    y1 = signal.upfirdn(h, dev(x), up, down, ctx=old)
+    old.sync()
+    assert old.get_option("gen_tiled_launches") == 0
+    assert float((y1 - y).abs().max()) <= 2 * tol(h, x)
+    # resample_poly window (n_pre_remove offset) through the same kernel
+    w = signal.kaiser_lowpass(up, down) if max(up, down) <= 160 else h
+    yr = signal.resample_poly(dev(x), up, down, w, ctx=ctx)
+    ctx.sync()
+    assert np.abs(yr.cpu().numpy() - O.resample_poly(x, up, down, w)).max() <= tol(w * up, x, 2.0)
+
+
 def test_upfirdn_tile_kernel_is_the_one_that_runs():
     """The templated rates must be served by ONE tile-kernel launch (not the generic fallback)."""
     rng = np.random.RandomState(1)
