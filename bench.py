@@ -112,7 +112,8 @@ class ClockSampler(threading.Thread):
             self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
             r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
-                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2,
+                     "sync_boost": 0x10, "display_clock_setting": 0x100}
             for nme, bit in names.items():
                 if r & bit:
                     self.reasons.add(nme)
