@@ -472,6 +472,8 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "toeplitz_chains")) return &o.toeplitz_chains;
     if (!strcmp(key, "toeplitz_ts")) return &o.toeplitz_ts;
     if (!strcmp(key, "toeplitz_stcs")) return &o.toeplitz_stcs;
+    if (!strcmp(key, "toeplitz_tn")) return &o.toeplitz_tn;
+    if (!strcmp(key, "toeplitz_tn_short")) return &o.toeplitz_tn_short;
     if (!strcmp(key, "ffma2")) return &o.ffma2;
     if (!strcmp(key, "filtfilt_fused")) return &o.filtfilt_fused;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;

@@ -40,6 +40,8 @@ struct Options {
     int64_t toeplitz_chains = 1; // accumulation chains per tile in TMEM (2: consecutive MMAs alternate accumulators; measured: no gain)
     int64_t filtfilt_fused = 1;  // padded filtfilt as ONE zero-phase pass with b (*) flip(b) when the pad covers k-1 samples (0: two passes)
     int64_t ffma2 = 1;           // FP32 direct kernels, K <= 256: packed FFMA2 core (0: scalar FFMA, the A/B arm)
+    int64_t toeplitz_tn = 0;     // tile width of the Toeplitz kernel: 0 auto, 64 or 128 columns
+    int64_t toeplitz_tn_short = 128; // auto: width for filters with K <= 129 (64 = deeper prefetch; measured in profiles/README.md)
     int64_t toeplitz_stcs = 0;   // 1: evict-first hint on the epilogue's output stores (A/B)
     int64_t toeplitz_ts = 1;     // 1: keep the first Toeplitz blocks in TMEM (A operand from TMEM); 0: all operands from shared memory
     int64_t toeplitz_loader = 0; // 0 auto (TMA-fed in-place buffers when they fit); 1 force the register-prefetch loader

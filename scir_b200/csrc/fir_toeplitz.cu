@@ -55,12 +55,12 @@ namespace scir_b200 {
 namespace {
 
 constexpr int TB = 128;                 // block length: MMA M, and the K extent of one p-block
-constexpr int TN = 128;                 // blocks (columns) per tile: MMA N
+constexpr int TN = 128;                 // blocks (columns) per tile: MMA N (the default; q.tn = 64 trades MMA width for deeper prefetch)
 constexpr int kEpiWarps = 4, kLoadWarps = 16;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMmaWarp = kEpiWarps + kLoadWarps, kTmaWarp = kMmaWarp + 1;
 constexpr int kToepThreads = (kEpiWarps + kLoadWarps + 2) * 32;
-constexpr int kMaxBuf = 3;
+constexpr int kMaxBuf = 6;
 constexpr int kPmaxLimit = 32;
 constexpr int RQMAX = ((TN + kPmaxLimit) * 32 + kLoadThreads - 1) / kLoadThreads;  // float4 chunks per loader thread
 
@@ -83,6 +83,7 @@ struct ToepParams {
     int mode;                           // MODE_REGISTER / MODE_INPLACE
     int nbuf;                           // slab buffers: 3 in place, 1 or 2 in register mode
     int fmt;                            // FMT_F16_SCALED / FMT_BF16
+    int tn;                             // columns per tile = MMA N: 128, or 64 (twice the buffers: deeper TMA prefetch)
     int chains;                         // independent accumulation chains per tile (1 or 2): accumulators = 2 stages * chains * 128 columns
     int ts_blocks;                      // Toeplitz blocks T_0 .. T_{ts_blocks-1} are kept in TMEM (A operand from TMEM)
     int tmem_cols;                      // TMEM allocation (power of two): accumulators, then the A blocks
@@ -189,10 +190,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 
 // kind::f16 instruction descriptor: D = F32 (bit 4), A/B format at bits 7 / 10 (0 = F16, 1 = BF16), both
 // K-major, N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t make_idesc(int fmt)
+__device__ __forceinline__ uint32_t make_idesc(int fmt, int tn)
 {
     const uint32_t ab = (fmt == FMT_BF16) ? 1u : 0u;
-    return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(TN >> 3) << 17) | (static_cast<uint32_t>(TB >> 4) << 24);
+    return (1u << 4) | (ab << 7) | (ab << 10) | (static_cast<uint32_t>(tn >> 3) << 17) | (static_cast<uint32_t>(TB >> 4) << 24);
 }
 
 // ---- virtual input sequence (same rules as fir_direct.cu: zero / held boundary, odd / even / const ext) ----
@@ -342,7 +343,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // raw_full[3] slab_full[3] buf_empty[3] acc_full[2] acc_empty[2]
-    __shared__ __align__(8) unsigned long long bars[3 * kMaxBuf + 4];
+    __shared__ __align__(8) unsigned long long bars[3 * kMaxBuf + 4];      // kMaxBuf = 6
     __shared__ uint32_t tmem_base_holder;
     __shared__ uint32_t red_slots[2][kLoadWarps];          // per-warp max|x| bits, double-buffered by tile parity
     __shared__ float inv_scale_ring[8];                    // loader -> epilogue: 1 / slab scale of tile it & 7 (a loader can be
@@ -358,7 +359,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q)
     const uint32_t bar0 = smem_u32(&bars[0]);
     enum { RAW_FULL = 0, SLAB_FULL = kMaxBuf, BUF_EMPTY = 2 * kMaxBuf, ACC_FULL = 3 * kMaxBuf, ACC_EMPTY = 3 * kMaxBuf + 2 };
     auto BAR = [&](int which, int idx) { return bar0 + 8u * static_cast<uint32_t>(which + idx); };
-    const int tile_cols = TN + q.pmax;
+    const int tile_cols = q.tn + q.pmax;
     const uint32_t raw_bytes = static_cast<uint32_t>(tile_cols) * TB * 4u;        // one fp32 tile incl. halo columns
     const uint32_t tmem_cols = static_cast<uint32_t>(q.tmem_cols);
     const uint32_t a_col0 = 2u * TN * static_cast<uint32_t>(q.chains);             // A blocks follow the accumulators
@@ -368,7 +369,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q)
         const long long lo = tile_lo(ipA);
         return q.fast_ok && lo >= q.fast_lo && lo + static_cast<long long>(tile_cols) * TB <= q.fast_hi;
     };
-    auto tile_ipA = [&](int ct) { return (q.first_col + static_cast<long long>(ct) * TN - q.pmax) * TB - q.org; };
+    auto tile_ipA = [&](int ct) { return (q.first_col + static_cast<long long>(ct) * q.tn - q.pmax) * TB - q.org; };
 
     // ---- one-time set-up: barriers, TMEM, the 8x-expanded (Hankel) tap arrays ------------------------------
     if (tid == 0) {
@@ -608,7 +609,7 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q)
     } else if (warp == kMmaWarp) {
         // ===== MMA ISSUER ===================================================================================
         const bool leader = elect_one();
-        const uint32_t idesc = make_idesc(q.fmt);
+        const uint32_t idesc = make_idesc(q.fmt, q.tn);
         const uint32_t a_lo0 = desc_lo(smem0, 128u);
         const uint32_t hank16 = hank_bytes >> 4, ver16 = ver_bytes >> 4;
         const uint32_t lbo_x = static_cast<uint32_t>(q.slab_cols) * 16u;
@@ -649,18 +650,18 @@ fir_toeplitz_kernel(const __grid_constant__ ToepParams q)
             const uint32_t apar = (it >> 1) & 1;
             const int row = t / q.tiles_per_row;
             const int ct = t - row * q.tiles_per_row;
-            const long long j0 = q.first_col + static_cast<long long>(ct) * TN;
+            const long long j0 = q.first_col + static_cast<long long>(ct) * q.tn;
             float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
             mbar_wait(BAR(ACC_FULL, acc), apar);
             tc_fence_after();
             // un-scale: exact powers of two (1 in BF16 mode); written by the loaders long before ACC_FULL
             const float inv_x = F16 ? *(volatile float*)&inv_scale_ring[it & 7] : 1.f;
             const float inv_c = q.tap_inv;
-            const long long ip_first = j0 * TB - q.org, ip_last = (j0 + TN) * TB - q.org;      // this tile's outputs [first, last)
+            const long long ip_first = j0 * TB - q.org, ip_last = (j0 + q.tn) * TB - q.org;      // this tile's outputs [first, last)
             const bool interior = ip_first >= q.ip_lo && ip_last <= q.ip_hi;
             const uint32_t tbase = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc) * acc_cols;
 #pragma unroll 1
-            for (int c4 = 0; c4 < TN / 32; ++c4) {
+            for (int c4 = 0; c4 < q.tn / 32; ++c4) {
                 uint32_t v[32];
                 tmem_ld32(tbase + static_cast<uint32_t>(c4 * 32), v);
                 if (q.chains == 2) {                       // second accumulation chain
@@ -732,10 +733,10 @@ __global__ void __launch_bounds__(256) toeplitz_fixup_kernel(const __grid_consta
             const int t = base + j;
             const int row = t / q.tiles_per_row;
             const int ct = t - row * q.tiles_per_row;
-            const long long ip0 = (q.first_col + static_cast<long long>(ct) * TN) * TB - q.org;
+            const long long ip0 = (q.first_col + static_cast<long long>(ct) * q.tn) * TB - q.org;
             const float* __restrict__ xr = p.x + static_cast<long long>(row) * p.ld_x;
             float* __restrict__ yr = p.y + static_cast<long long>(row) * p.ld_y + p.out_off;
-            for (int o = threadIdx.x; o < TB * TN; o += blockDim.x) {
+            for (int o = threadIdx.x; o < TB * q.tn; o += blockDim.x) {
                 const long long ip = ip0 + o;
                 if (ip < q.ip_lo || ip >= q.ip_hi) continue;
                 const long long i = map_index(p, ip);                  // virtual index of this output
@@ -762,7 +763,11 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
     q.pmax = static_cast<int>((k - 1 + (TB - 1)) / TB);
     if (q.pmax > kPmaxLimit) return false;                 // loader register budget (RMAX) and shared memory
     q.hank_cores = 16 * q.pmax + 31;
-    q.slab_cols = (TN + q.pmax) | 1;
+    // tile width: 64 columns give twice as many (half-size) buffers for the in-place pipeline, i.e. a deeper TMA
+    // prefetch, at half the MMA width: only for filters short enough to be HBM-bound (toeplitz_tn: 0 auto, 64, 128)
+    q.tn = (ctx->opt.toeplitz_tn == 64) ? 64 : (ctx->opt.toeplitz_tn == 128) ? TN : ((q.pmax <= 1) ? ctx->opt.toeplitz_tn_short : TN);
+    if (q.tn != 64) q.tn = TN;
+    q.slab_cols = (q.tn + q.pmax) | 1;
     q.fmt = (ctx->opt.toeplitz_split == 1) ? FMT_BF16 : FMT_F16_SCALED;
     int64_t terms = ctx->opt.toeplitz_terms;
     if (terms != 3 && terms != 4 && terms != 6) terms = 3;
@@ -781,13 +786,13 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
     }
     const size_t hank = static_cast<size_t>(q.hank_cores) * 128 * q.nver;
     const size_t slab = static_cast<size_t>(16) * q.slab_cols * 16 * q.nver;
-    const size_t raw = static_cast<size_t>(TN + q.pmax) * TB * 4;
+    const size_t raw = static_cast<size_t>(q.tn + q.pmax) * TB * 4;
     const size_t budget = static_cast<size_t>(ctx->max_smem_optin) - 1024;        // static smem + slack
     auto up128 = [](size_t v) { return (v + 127) / 128 * 128; };
     if (ctx->opt.toeplitz_loader != 1 && hank + 3 * up128(std::max(slab, raw)) <= budget) {
         q.mode = MODE_INPLACE;                             // short filters: TMA-fed buffers converted in place
-        q.nbuf = 3;
         q.buf_bytes = static_cast<unsigned>(up128(std::max(slab, raw)));
+        q.nbuf = static_cast<int>(std::min<size_t>(kMaxBuf, (budget - hank) / q.buf_bytes));
     } else {
         q.mode = MODE_REGISTER;                            // long filters: register prefetch
         q.buf_bytes = static_cast<unsigned>(up128(slab));
@@ -816,9 +821,9 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
         const long long al0 = (pass.dir > 0) ? pass.in_off : -(pass.n_v + pass.in_off);
         q.org = ((al0 % 4) + 4) % 4;
     }
-    const long long tile_len = static_cast<long long>(TB) * TN;
+    const long long tile_len = static_cast<long long>(TB) * q.tn;
     const long long first_tile = (q.ip_lo + q.org) / tile_len;          // ip + org >= 0 is the block-grid coordinate
-    q.first_col = first_tile * TN;
+    q.first_col = first_tile * q.tn;
     const long long tiles = (q.ip_hi + q.org + tile_len - 1) / tile_len - first_tile;
     if (tiles <= 0 || tiles * pass.batch > 0x7fffffffLL) return false;
     q.tiles_per_row = static_cast<int>(tiles);
