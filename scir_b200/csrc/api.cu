@@ -118,7 +118,7 @@ static int check_taps(const float* taps, int64_t k)
 // K >= toeplitz_min_k (1024) always takes the tensor path, where the direct kernel is 7x slower at any size
 // that matters.  The direct kernel's own streaming floor (~5.2 TB/s) means large launches go to the tensor
 // path even for short filters: there it is simply the better streaming kernel.
-static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t tiles)
+static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t tiles, bool aligned)
 {
     // fitted to tools/sweep_dispatch.py on B200 (45 shapes, K = 48 .. 511, 64 .. 16384 tiles; profiles/README.md):
     //   direct:   14 us + per 16384 outputs max(25 ns [its streaming floor, ~5.2 TB/s], (2K + 29) flop / 72 TFLOP/s)
@@ -131,7 +131,9 @@ static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64
     const double t_round = std::max(3.6e-6, static_cast<double>(3 * ksteps) * 58e-9);
     const double rounds = std::ceil(static_cast<double>(tiles) / static_cast<double>(ctx->sm_count));
     const double t_toep = std::max(20e-6, 16e-6 + rounds * t_round);
-    return t_toep < t_direct;
+    // rows that are not 16-byte aligned (odd views / pitches) lose the bulk-copy staging in both families: measured
+    // (tools/time_unaligned.py, 256 x 2^18) x1.7 on the tensor kernel, x1.0-1.4 on the direct kernel
+    return aligned ? (t_toep < t_direct) : (1.7 * t_toep < 1.2 * t_direct);
 }
 
 int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
@@ -139,9 +141,10 @@ int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t 
     const int64_t mode = ctx->opt.long_tap_path;
     if (mode != 1 && ctx->opt.variant == 0) {
         int64_t tiles = 0;
-        if (toeplitz_supported(ctx, pass, k, &tiles)) {
+        bool aligned = false;
+        if (toeplitz_supported(ctx, pass, k, &tiles, &aligned)) {
             const bool want = (mode == 2) || k >= ctx->opt.toeplitz_min_k ||
-                              (k >= ctx->opt.toeplitz_min_k_full && prefer_toeplitz(ctx, pass, k, tiles));
+                              (k >= ctx->opt.toeplitz_min_k_full && prefer_toeplitz(ctx, pass, k, tiles, aligned));
             if (want) return launch_fir_toeplitz(ctx, pass, c, k);
         }
     }

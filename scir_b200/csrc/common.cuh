@@ -133,7 +133,7 @@ int launch_upfirdn(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up
                    int64_t ld_y, int64_t m_begin, int64_t m_count, int ext_mode = 0, float cval = 0.f);
 
 // ---- long-tap tensor-core path (tcgen05 block-Toeplitz) -----------------------------------------
-bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles = nullptr);
+bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles = nullptr, bool* aligned = nullptr);
 int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 
 int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);

@@ -842,11 +842,12 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
 
 }  // namespace
 
-bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles)
+bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles, bool* aligned)
 {
     ToepPlan plan;
     if (!(pass.batch > 0 && pass.out_end > pass.out_begin && make_plan(ctx, pass, nullptr, k, &plan))) return false;
-    if (tiles) *tiles = plan.q.total_tiles;
+    if (tiles) *tiles = static_cast<int64_t>(plan.q.total_tiles) * plan.q.tn / TN;     // in units of 128 x 128 outputs
+    if (aligned) *aligned = plan.q.fast_ok != 0;
     return true;
 }
 
