@@ -22,6 +22,12 @@
 //     overlaps its neighbours' FFMA streams; no tracing compiler, no software pipeline needed.
 //   * tap counts of any size run the same code: a runtime loop over chunks of KC taps
 //     (`LDCU UR, c[0x0][UR+imm]`), halo = nchunk*KC samples.
+//   * for K <= 256 the inner product is issued as packed FFMA2 (fir_core2): two outputs per issue slot, the
+//     sample broadcast, two consecutive taps from a uniform-register pair -- half the issue slots for the same
+//     FMA pipe rate, so loads and loop control stop costing FP32 throughput (config 2: 2.75 -> 2.25 ms).
+//
+// Since the tcgen05 Toeplitz kernel (fir_toeplitz.cu) takes every large launch, this family serves small and
+// mid-size launches (api.cu: prefer_toeplitz) and the A/B arms.
 //
 // The same kernel serves lfilter / filtfilt: direction (causal / anticausal), boundary rule
 // (zero state or held end value = SciPy's lfilter_zi steady state) and odd/even/constant signal

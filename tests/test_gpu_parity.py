@@ -170,7 +170,7 @@ def test_stream_kernel_many_tiles_per_cta(k, variant):
 @pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_kernel_variants_agree(variant):
     """variant 1 = generic (non-bulk) IO, 2 = naive 1-thread/output kernel, 3 = one-tile-per-CTA kernel,
-    4 = CTA-streaming kernel, 5/6 = warp-streaming kernel with 20/28 outputs per thread."""
+    4 = CTA-streaming kernel (scalar FFMA core)."""
     rng = np.random.RandomState(5)
     x = (rng.rand(3, 15000).astype(np.float32) * 2 - 1)
     taps = rng.randn(100).astype(np.float32)
