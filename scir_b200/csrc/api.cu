@@ -724,14 +724,14 @@ int scir_b200_resample_poly_pad_f32(scir_b200_ctx* ctx, const float* window, int
     SCIR_TRY(check_no_alias(d_x, ld_x, n_in, d_y, ld_y, n_out, batch));
     if (padtype >= SCIR_B200_EXT_CONSTANT && padtype <= SCIR_B200_EXT_LINE)
         return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y, padtype, cval);
-    if (padtype == SCIR_B200_PAD_STAT_MEDIAN)
-        return set_error(SCIR_B200_ERR_UNSUPPORTED, "resample_poly padtype='median' has no device implementation yet");
-    if (padtype != SCIR_B200_PAD_STAT_MEAN && padtype != SCIR_B200_PAD_STAT_MINIMUM && padtype != SCIR_B200_PAD_STAT_MAXIMUM)
+    if (padtype != SCIR_B200_PAD_STAT_MEAN && padtype != SCIR_B200_PAD_STAT_MINIMUM && padtype != SCIR_B200_PAD_STAT_MAXIMUM &&
+        padtype != SCIR_B200_PAD_STAT_MEDIAN)
         return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown padtype %d", padtype);
     if (batch == 0 || n_in == 0 || copy)          // SciPy returns x.copy() before looking at padtype (:3885-3886)
         return resample_device(ctx, window, len_h, up, down, d_x, ld_x, batch, n_in, d_y, ld_y);
     // background statistic per row, x - bg into scratch, zero-padded upfirdn, + bg (:3927-3957)
-    const int stat = (padtype == SCIR_B200_PAD_STAT_MEAN) ? 0 : (padtype == SCIR_B200_PAD_STAT_MINIMUM ? 1 : 2);
+    const int stat = (padtype == SCIR_B200_PAD_STAT_MEAN) ? 0 : (padtype == SCIR_B200_PAD_STAT_MINIMUM) ? 1
+                   : (padtype == SCIR_B200_PAD_STAT_MAXIMUM) ? 2 : 3;
     const int64_t ldc = (n_in + 3) / 4 * 4;
     SCIR_TRY(ctx_scratch(ctx, ctx->row_bg, static_cast<size_t>(batch) * sizeof(float)));
     SCIR_TRY(ctx_scratch(ctx, ctx->scratch, static_cast<size_t>(batch) * ldc * sizeof(float)));

@@ -128,13 +128,75 @@ __global__ void __launch_bounds__(256) row_offset_kernel(const float* x, long lo
         yr[i] = __fadd_rn(xr[i], b);
 }
 
+// ---- per-row median (resample_poly padtype='median'): exact k-th order statistics by radix select -----------
+// One CTA per row.  Floats map to unsigned keys that sort like the values; four passes of an 8-bit histogram over
+// the elements that still match the selected prefix pin down the k-th smallest key exactly.  Even n: numpy's
+// median is the f32 mean of the two middle values (np.mean of two f32 -> (a + b) / 2 in f32), so two selections.
+__device__ __forceinline__ uint32_t f32_sort_key(float v)
+{
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_sort_key(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ float row_select(const float* __restrict__ xr, long long n, long long kth, unsigned* hist, unsigned* sh_state)
+{
+    uint32_t prefix = 0, mask = 0;
+    long long k = kth;                                     // rank among the elements matching the prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = f32_sort_key(xr[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = 0;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (acc + hist[b] > k) break;
+                acc += hist[b];
+            }
+            sh_state[0] = static_cast<unsigned>(b);
+            sh_state[1] = static_cast<unsigned>(k - acc);  // fits: a row has < 2^32 elements per bin (n checked by the host)
+        }
+        __syncthreads();
+        prefix |= sh_state[0] << shift;
+        mask |= 255u << shift;
+        k = sh_state[1];
+        __syncthreads();
+    }
+    return f32_from_sort_key(prefix);
+}
+
+__global__ void __launch_bounds__(1024) row_median_kernel(const float* __restrict__ x, long long ld_x, long long n, float* __restrict__ out)
+{
+    __shared__ unsigned hist[256];
+    __shared__ unsigned state[2];
+    const float* xr = x + static_cast<long long>(blockIdx.x) * ld_x;
+    const float hi = row_select(xr, n, n / 2, hist, state);
+    float med = hi;
+    if ((n & 1) == 0) {
+        const float lo = row_select(xr, n, n / 2 - 1, hist, state);
+        med = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = med;
+}
+
 int launch_row_stat(scir_b200_ctx* ctx, int stat, const float* d_x, int64_t ld_x, int64_t batch, int64_t n, float* d_out)
 {
     if (batch == 0) return SCIR_B200_OK;
     SCIR_TRY(ctx_bind(ctx));
     if (batch > 0x7fffffffLL) return set_error(SCIR_B200_ERR_UNSUPPORTED, "too many rows");
     const unsigned g = static_cast<unsigned>(batch);
-    if (stat == STAT_MEAN) row_stat_kernel<STAT_MEAN><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
+    if (stat == 3) {                                       // median
+        if (n >= (1LL << 32)) return set_error(SCIR_B200_ERR_UNSUPPORTED, "median: rows of 2^32 samples or more");
+        row_median_kernel<<<g, 1024, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
+    } else if (stat == STAT_MEAN) row_stat_kernel<STAT_MEAN><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
     else if (stat == STAT_MIN) row_stat_kernel<STAT_MIN><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
     else row_stat_kernel<STAT_MAX><<<g, 512, 0, ctx->stream>>>(d_x, ld_x, n, d_out);
     SCIR_CUDA(cudaGetLastError(), "row_stat_kernel launch");

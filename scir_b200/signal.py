@@ -204,7 +204,7 @@ _PAD_STATS = {"mean": L.PAD_STAT_MEAN, "median": L.PAD_STAT_MEDIAN, "minimum": L
 
 def resample_poly(x, up, down, window=("kaiser", 5.0), padtype="constant", cval=None, *, ctx=None):
     """resample_poly(x, up, down, window, padtype, cval) along the last axis (scipy/signal/_signaltools.py:3865-3957).
-    padtype: an upfirdn extension mode, or 'mean' / 'minimum' / 'maximum' ('median' raises: no device kernel yet)."""
+    padtype: an upfirdn extension mode, or 'mean' / 'median' / 'minimum' / 'maximum'."""
     if int(up) != up or int(down) != down:
         raise ValueError("up and down must be integers")
     up, down = int(up), int(down)

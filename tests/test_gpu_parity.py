@@ -488,10 +488,6 @@ def test_resample_poly_padtypes_golden(scipy_modes):
     for i, (up, down, lh, n) in enumerate(v["rcases"]):
         h, x = v[f"r{i}_h"], v[f"r{i}_x"]
         for pt in [str(s) for s in v["padtypes"]]:
-            if pt == "median":
-                with pytest.raises(gpu.GpuError):
-                    signal.resample_poly(dev(x), int(up), int(down), h, padtype=pt)
-                continue
             want = v[f"r{i}_{pt}"]
             for xin in (x, dev(x)):
                 y = signal.resample_poly(xin, int(up), int(down), h, padtype=pt)
@@ -511,10 +507,35 @@ def test_resample_poly_stat_padtypes_at_scale():
     from scipy.signal import firwin
     h = firwin(96, 1.0 / 3.0, window=("kaiser", 5.0)).astype(np.float32)
     x = (rng.rand(5, 50000).astype(np.float32) + 2.0)
-    for pt in ("mean", "minimum", "maximum", "line", "edge"):
+    x[2, ::3] -= 5.0                                         # negative values, ties and an even / odd split below
+    x[3, :1000] = 2.5
+    for pt in ("mean", "median", "minimum", "maximum", "line", "edge"):
         want = O.resample_poly_padtype(x, 3, 2, h, pt)
         y = signal.resample_poly(dev(x), 3, 2, h, padtype=pt).cpu().numpy()
         assert np.abs(y - want).max() <= tol(h * 3, x, 4.0), pt
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 1001, 4096, 100000])
+def test_row_median_is_exact(n):
+    """The median behind padtype='median' is an exact order statistic (radix select), including negative values,
+    ties, zeros of both signs and even lengths (f32 mean of the two middle values, like numpy).  A zero filter
+    makes resample_poly return the statistic itself: y = upfirdn(0, x - med) + med = med."""
+    rng = np.random.RandomState(n)
+    x = rng.randn(6, n).astype(np.float32)
+    x[1] = np.round(x[1] * 2) / 2                           # many ties
+    x[2] = -np.abs(x[2])
+    x[3, : n // 2] = 0.0
+    x[4, ::2] = -0.0
+    x[5] *= 1e30
+    zero = np.zeros(3, np.float32)
+    y = signal.resample_poly(dev(x), 2, 1, zero, padtype="median").cpu().numpy()
+    want = np.median(x, axis=1).astype(np.float32)
+    assert y.shape == (6, 2 * n)
+    for r in range(6):
+        assert np.all(y[r] == want[r]), (r, y[r][:3], want[r])
+    for pt, fn in (("minimum", np.amin), ("maximum", np.amax)):
+        y = signal.resample_poly(dev(x), 2, 1, zero, padtype=pt).cpu().numpy()
+        assert np.array_equal(y[:, 0], fn(x, axis=1))
 
 
 def test_upfirdn_windowed_output():
