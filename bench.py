@@ -384,7 +384,10 @@ def main():
         in_bytes, out_bytes = rows * n * 4, rows * n_out * 4
         hx, hy = C.c_void_p(), C.c_void_p()
         rc1, rc2 = lib.scir_b200_host_alloc(in_bytes, C.byref(hx)), lib.scir_b200_host_alloc(out_bytes, C.byref(hy))
-        if rc1 == 0 and rc2 == 0:
+        alloc_ok = torch.tensor([1 if (rc1 == 0 and rc2 == 0) else 0], device=dev, dtype=torch.int32)
+        if world > 1:                                      # every rank takes the same branch (barriers inside)
+            dist.all_reduce(alloc_ok, op=dist.ReduceOp.MIN)
+        if int(alloc_ok.item()) == 1:
             ax = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=(rows, n))
             ay = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(rows, n_out))
             ax[:] = x.cpu().numpy()
@@ -427,7 +430,7 @@ def main():
             if rc != 0:
                 e2e["error"] = L.last_error()
         else:
-            e2e = {"value": None, "unit": UNIT, "error": L.last_error()}
+            e2e = {"value": None, "unit": UNIT, "error": L.last_error() or "pinned host allocation failed on another rank"}
         if hx:
             lib.scir_b200_host_free(hx)
         if hy:
