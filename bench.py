@@ -1,31 +1,40 @@
 #!/usr/bin/env python3
 """bench.py -- batched FIR output Gsamples/s on N B200s (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1..c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1..c5] [--no-sweep]
 
-A step = one pass of the hot path over one batch of synthetic input.  Default workload is
-BASELINE.json configs[1] ("c2"): lfilter(b, [1], x), 1024 channels x 2^20 samples, 63 taps, f32.
-N > 1: one process per GPU (torchrun), channels sharded across ranks, no data-path collective
-(rows are independent); per-GPU work is fixed => weak scaling, value = all ranks' samples / max time.
+A step = one pass of the hot path over one batch of synthetic input.  The headline workload is BASELINE.json
+configs[1] ("c2"): lfilter(b, [1], x), 1024 channels x 2^20 samples, 63 taps, f32.  N > 1: one process per GPU
+(torchrun), channels sharded across ranks, no data-path collective (rows are independent); per-GPU work is fixed
+=> weak scaling, value = all ranks' samples / max-over-ranks time.
 
-One JSON line is printed by rank 0.  Keys beyond the base contract:
-  roofline      the dominant kernel against the roofline that bounds it.  HBM-bound launches (config 2 on
-                the tcgen05 Toeplitz kernel, config 4): algorithmic bytes / CUDA-event launch time against
-                the measured HBM peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback).  Tensor-bound
-                launches (configs 3, 5): executed tensor-pipe TFLOP/s against the measured dense-bf16 peak.
-                `tensor`, `fp32` and `shape_roofline` (BASELINE.md's max(bytes/HBM, 2K flops/FP32)) explain it.
-  cpu_baseline  the CPU restatement of the reference loop (oracle/, kind "port") timed here on the
-                host cores over a bounded row sample.
-  e2e           the same metric through the host-array C-ABI call (pinned host buffers, H2D+kernel+D2H
-                inside the timed region).
-`--impl reference` times the reference's own CPU implementation (its Rust cannot be built here: no
-cargo/rustc, so the oracle port, all host threads) on a bounded sample of the same workload.
+ONE JSON line is printed by rank 0.  Keys beyond the base contract:
+  roofline      the dominant kernel against the roofline that bounds it.  HBM-bound launches (config 2 on the
+                tcgen05 Toeplitz kernel, config 4): algorithmic bytes / CUDA-event launch time against the measured
+                HBM peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback).  Tensor-bound launches (configs 3, 5):
+                executed tensor-pipe TFLOP/s against the measured dense-bf16 peak.  `tensor`, `fp32` and
+                `shape_roofline` (BASELINE.md's max(bytes/HBM, 2K flops/FP32)) explain it.
+  parity        GPU result of the LAST timed step against the f64-accumulating oracle on <= 6 rows of the same
+                buffers: max|err|, the tolerance 1e-5 * sum|h| * max|x| (north_star), and their ratio.
+  configs       the same record (ms_per_step, value, roofline, clocks with throttle reasons, parity) for EVERY
+                BASELINE config c1..c5, measured in this run after the headline (skipped with --no-sweep).
+  strong        N > 1 only: BASELINE configs[1] and configs[4] as FIXED problems split over the N GPUs
+                (rows/N per GPU), with efficiency against the one-GPU time of the whole problem measured in this run.
+  cpu_baseline  the CPU restatement of the reference loop (oracle/, kind "port") timed here on the host cores
+                over a bounded row sample (N = 1 only).
+  e2e           the same metric through the host-array C-ABI call (pinned host buffers, H2D + kernel + D2H inside
+                the timed region), plus `pageable` (the same call on plain malloc'd arrays, what a Rust Vec or numpy
+                array is), `ceiling` (what concurrent plain pinned copies of the same volume reach on this box, all
+                ranks at once) and, at N > 1, `mg` (rank 0 alone drives all N GPUs through scir_b200_mg_*_host).
+`--impl reference` times the reference's own CPU implementation (its Rust cannot be built here: no cargo/rustc, so
+the oracle port, all host threads) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import sys
 import threading
@@ -40,6 +49,7 @@ if ROOT not in sys.path:
 METRIC = "batched FIR output Gsamples/s"
 UNIT = "Gsamples/s"
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.45, BASELINE.md section 2
+L2_BYTES = 126e6
 
 
 def firwin_np(ntaps, cutoff, window="hamming", beta=5.0):
@@ -63,6 +73,8 @@ CONFIGS = {
     # SURVEY 8(f).1 (not a BASELINE config): DeviceArray add_scalar_auto on device-resident data, 2^30 elements
     "e1": dict(rows=1024, n=1 << 20, k=1, op="ew", desc="DeviceArray add_scalar_auto, 2^30 f32 elements (8 B/element)"),
 }
+BASELINE_CONFIGS = ("c1", "c2", "c3", "c4", "c5")
+STRONG_CONFIGS = ("c2", "c5")          # BASELINE configs[1] "on 1 and 8 B200", configs[4] "scaling sweep 1/2/4/8"
 
 
 def make_taps(cfg):
@@ -77,11 +89,17 @@ def make_taps(cfg):
     return firwin_np(cfg["k"], 0.2)
 
 
+def out_len(cfg):
+    if cfg["op"] == "resample":
+        return -(-cfg["n"] * cfg["up"] // cfg["down"])
+    return cfg["n"]
+
+
 def algorithmic(cfg, rows):
     """(out samples, bytes, flops) per step per GPU -- SURVEY.md 8(d) per-output figures."""
     n, k = cfg["n"], cfg["k"]
     if cfg["op"] == "resample":
-        n_out = -(-n * cfg["up"] // cfg["down"])
+        n_out = out_len(cfg)
         outs = rows * n_out
         return outs, rows * (n * 4 + n_out * 4), outs * 2.0 * k / cfg["up"]
     outs = rows * n
@@ -90,12 +108,28 @@ def algorithmic(cfg, rows):
     return outs, outs * 8.0, outs * 2.0 * k
 
 
+def config_dict(name, cfg, rows, world):
+    """The workload description both arms print (identical for --impl ours and --impl reference)."""
+    _, abytes, _ = algorithmic(cfg, rows)
+    return {"workload": cfg["desc"], "config": name, "rows_per_gpu": rows, "n": cfg["n"], "taps": cfg["k"],
+            "global_rows": rows * world, "sharding": f"rows x{world}, no collective",
+            "l2": "inputs larger than L2 (per-step working set >> 126 MB)" if abytes > 3e8 else
+                  "working set fits L2: steps rotate over input/output buffer pairs totalling > 400 MB, so every "
+                  "step reads cold data"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+    """Samples SM clock, throttle reasons and board power with NVML while a timed region runs."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2, "sync_boost": 0x10,
+               "display_clock_setting": 0x100}
+    REJECT = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.power_w, self.mask = [], 0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -111,26 +145,50 @@ class ClockSampler(threading.Thread):
         try:
             self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
             r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
-                     "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2,
-                     "sync_boost": 0x10, "display_clock_setting": 0x100}
-            for nme, bit in names.items():
+            self.mask |= int(r)
+            for nme, bit in self.REASONS.items():
                 if r & bit:
                     self.reasons.add(nme)
+            self.power_w.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
         except Exception:
             pass
 
     def run(self):
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def result(self):
         self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        med = float(np.median(self.samples))
+        reasons = sorted(self.reasons)
+        out = {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples),
+               "sm_mhz_min": float(min(self.samples)), "reason_mask": hex(self.mask),
+               "power_w_max": max(self.power_w) if self.power_w else None}
+        # a median well below max MUST carry its reason: NVML reports the power cap only while it is being
+        # applied, and a 2 ms poll can miss it -- board power at the limit says the same thing
+        if self.max_mhz and med < 0.93 * self.max_mhz and not reasons:
+            try:
+                lim = self.nv.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                lim = None
+            out["power_limit_w"] = lim
+            if lim and self.power_w and max(self.power_w) >= 0.9 * lim:
+                out["reasons"] = ["sw_power_cap"]
+                out["reasons_inferred"] = f"board power {max(self.power_w):.0f} W at the {lim:.0f} W limit"
+            else:
+                out["reasons"] = ["unexplained_low_clock"]
+        return out
+
+    @staticmethod
+    def rejected(clocks):
+        if not clocks or clocks.get("sm_mhz") is None:
+            return False
+        return any(r in ClockSampler.REJECT for r in clocks["reasons"]) or "unexplained_low_clock" in clocks["reasons"]
 
 
 def measured_peaks():
@@ -160,71 +218,472 @@ def run_step(cfg, signal_mod, gpu_mod, x, taps, out):
     return signal_mod.filtfilt(taps, [1.0], x)
 
 
-def cpu_reference_rate(cfg, taps, threads, budget_s):
-    """Times the oracle port of the reference loop (gpu/lib.rs:1134-1152) over a bounded row sample.
-    Returns (Gsamples/s, rows, seconds)."""
+# ---- parity of a finished step against the oracle (checker only) ---------------------------
+def parity_check(cfg, taps, x_dev, y_dev):
+    """max|err| of rows of the GPU result against the f64-accumulating oracle, with the north_star tolerance
+    1e-5 * sum|h| * max|x|.  <= 6 rows; config 3 (4097 taps) is checked on two windows per row (the filter is
+    causal: a window plus its K-1 history reproduces those outputs exactly)."""
     from oracle import oracle as O
-    n, k = cfg["n"], cfg["k"]
-    rng = np.random.RandomState(42)
-    # calibrate on one row per thread, then size the sample for ~budget_s
-    rows = max(1, threads)
-    x = (rng.rand(rows, n).astype(np.float32) * 2 - 1)
+    rows_total, n = x_dev.shape
+    rows = sorted(set([0, 1, rows_total // 2, rows_total - 2, rows_total - 1]) & set(range(rows_total)))
+    if cfg["op"] == "fir":
+        rows = sorted(set(rows + [rows_total // 3]))
+    xs = x_dev[rows].cpu().numpy()
+    ys = y_dev[rows].cpu().numpy().astype(np.float64)
+    xmax = float(np.abs(xs).max())
+    op, k = cfg["op"], cfg["k"]
+    t64 = taps.astype(np.float64)
+    rec = {"rows": len(rows), "oracle": "f64 accumulation of the f32 data (oracle/fir_oracle.c)"}
+    if op in ("fir", "lfilter"):
+        kt = taps if op == "fir" else taps[::-1].copy()         # oracle takes the reference's tap order
+        tol = 1e-5 * float(np.abs(t64).sum()) * xmax
+        if k > 1024 and n > (1 << 17):
+            L = 1 << 15
+            err = 0.0
+            for s in (0, n // 2 - 12345, n - L):
+                lo = max(0, s - (k - 1))
+                want = O.fir1d_batched_f32_acc64(xs[:, lo:s + L], kt)[:, s - lo:]
+                err = max(err, float(np.abs(ys[:, s:s + L] - want).max()))
+            rec["windows"] = f"3 windows of {L} outputs per row (start, middle, end)"
+        else:
+            err = float(np.abs(ys - O.fir1d_batched_f32_acc64(xs, kt)).max())
+        rec.update(max_err=err, tol=tol)
+    elif op == "resample":
+        up = cfg["up"]
+        h = t64 * up
+        tol = 1e-5 * max(float(np.abs(h[t::up]).sum()) for t in range(up)) * xmax      # the taps one output uses
+        want = O.resample_poly(xs, cfg["up"], cfg["down"], taps, acc64=True)
+        rec.update(max_err=float(np.abs(ys - want).max()), tol=tol,
+                   tol_note="sum|h| over the taps of one output phase (h = window * up), the largest phase")
+    else:   # filtfilt, odd padding: zero-phase filter hc = b (*) flip(b); the odd extension reaches 3 max|x| at the edges
+        hc = np.convolve(t64, t64[::-1])
+        tol = 1e-5 * float(np.abs(hc).sum()) * xmax
+        want = O.filtfilt_fir(taps, xs, O.PAD_ODD, -1)
+        edge = 3 * k + 2 * k
+        d = np.abs(ys - want)
+        rec.update(max_err=float(d[:, edge:n - edge].max()), tol=tol,
+                   edges={"max_err": float(max(d[:, :edge].max(), d[:, n - edge:].max())), "tol": 3.0 * tol,
+                          "note": "within padlen + 2K of either end the odd extension 2*x[0] - x[i] reaches 3 max|x|"})
+        rec["edges"]["frac"] = rec["edges"]["max_err"] / rec["edges"]["tol"]
+    rec["frac"] = rec["max_err"] / rec["tol"] if rec["tol"] > 0 else None
+    rec["ok"] = bool(rec["max_err"] <= rec["tol"] and (("edges" not in rec) or rec["edges"]["max_err"] <= rec["edges"]["tol"]))
+    return rec
+
+
+# ---- one config, device-resident: CUDA events over exactly `steps` steps -----------------------------------------------
+class Env:
+    """Everything a measurement needs (torch, dist, library handles, rank info)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from scir_b200 import _lib as L
+        from scir_b200 import dist as sdist
+        from scir_b200 import gpu, signal
+        self.torch, self.dist, self.L, self.sdist, self.gpu, self.signal = torch, dist, L, sdist, gpu, signal
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
+        self.variant = args.variant
+        self.hbm_peak, self.peak_src, self.peaks = measured_peaks()
+        self.ffma_tflops = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(self, v):
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def executed_mma_flops_per_out(k, terms):
+    """What the tcgen05 Toeplitz kernel executes per output: per 128 x 128 tile, `terms` M128 N128 K16 MMAs for every
+    K step of every Toeplitz block that meets a non-zero tap (fir_toeplitz.cu: issue_tile)."""
+    pmax = (k - 1 + 127) // 128
+    ksteps = sum(8 - (max(0, 128 * pb - (k - 1)) >> 4) for pb in range(pmax + 1))
+    return terms * ksteps * (2.0 * 128 * 128 * 16) / (128 * 128), terms * ksteps
+
+
+def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=False):
+    """Times `steps` steps of one config with inputs resident in HBM.  Returns the record (and, with keep=True, the
+    tensors of the last step for the e2e cross-check)."""
+    torch = env.torch
+    n = cfg["n"]
+    taps = make_taps(cfg)
+    outs, abytes, aflops = algorithmic(cfg, rows)
+    nbuf = 1 if abytes > 3e8 else int(math.ceil(4e8 / max(abytes, 1)))
+    g = torch.Generator(device=env.dev).manual_seed(42 + env.rank)
+    xs = [torch.rand((rows, n), device=env.dev, generator=g) * 2 - 1 for _ in range(nbuf)]
+    outs_buf = [torch.empty_like(x) if cfg["op"] in ("fir", "lfilter", "ew") else None for x in xs]
+    ctx = env.gpu.torch_context(xs[0])
+    if env.variant:
+        ctx.set_option("variant", env.variant)
+    for key, val in env.opts.items():
+        ctx.set_option(key, val)
+
+    def timed(count):
+        sampler = ClockSampler(env.local_rank)
+        sampler.sample()
+        sampler.start()
+        l0, tc0, fx0 = ctx.launch_count(), ctx.get_option("toeplitz_launches"), ctx.get_option("fixup_launches")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = None
+        for i in range(count):
+            y = run_step(cfg, env.signal, env.gpu, xs[i % nbuf], taps, outs_buf[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.sample()
+        clocks = sampler.result()
+        return (e0.elapsed_time(e1) / count, clocks, ctx.launch_count() - l0, ctx.get_option("toeplitz_launches") - tc0,
+                ctx.get_option("fixup_launches") - fx0, y, (count - 1) % nbuf)
+
+    for i in range(warmup):
+        run_step(cfg, env.signal, env.gpu, xs[i % nbuf], taps, outs_buf[i % nbuf])
+    env.barrier()
+    ms, clocks, launches, tc_launches, fx_launches, y, last = timed(steps)
+    remeasured = False
+    if ClockSampler.rejected(clocks):                       # the contract: rejected once, measured again
+        env.barrier()
+        first = clocks
+        ms, clocks, launches, tc_launches, fx_launches, y, last = timed(steps)
+        clocks["first_attempt"] = {k: first.get(k) for k in ("sm_mhz", "reasons")}
+        remeasured = True
+    env.barrier()
+    ms_max = env.max_over_ranks(ms)
+    value = outs * env.world / (ms_max * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (events on the launching stream) ------------------------------------
+    tensor_path = tc_launches > 0
+    n_kern = max((launches - fx_launches) / steps, 1)       # dominant-kernel launches per step (two-pass filtfilt: 2)
+    kern_ms = ms / n_kern
+    achieved_gbs = abytes / (ms * 1e-3) / 1e9
+    achieved_tf = aflops / (ms * 1e-3) / 1e12
+    t_hbm = abytes / (env.hbm_peak * 1e9)
+    t_fp32 = aflops / (FP32_NOMINAL_TFLOPS * 1e12)
+    t_roof = max(t_hbm, t_fp32)
+    tensor, bound = None, "hbm"
+    if tensor_path:
+        terms = env.opts.get("toeplitz_terms", 3)
+        k, passes = cfg["k"], 1
+        if cfg["op"] == "filtfilt":
+            if tc_launches // steps == 1:                   # padded filtfilt fused into one zero-phase pass of 2K-1 taps
+                k = 2 * k - 1
+            else:
+                passes = 2
+        per_out, mma_per_tile = executed_mma_flops_per_out(k, terms)
+        exec_tf = outs * passes * per_out / (ms * 1e-3) / 1e12
+        tc_peak = float(env.peaks.get("bf16_tflops", 2250.0))
+        t_tensor = outs * passes * per_out / (tc_peak * 1e12)
+        tensor = {"split": ("fp16x%d block-scaled, fp32 accumulate in TMEM" % terms) if not env.opts.get("toeplitz_split") else
+                           ("bf16x%d, fp32 accumulate in TMEM" % terms),
+                  "executed_tflops": exec_tf, "peak_tflops": tc_peak,
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in env.peaks else "nominal 2250",
+                  "peak_sustained_tflops": env.peaks.get("bf16_tflops_sustained"),
+                  "frac_executed": exec_tf / tc_peak,
+                  "algorithmic_tflops": achieved_tf, "frac_algorithmic_x_terms": achieved_tf * terms / tc_peak,
+                  "mma_per_tile": mma_per_tile}
+        if t_tensor > t_hbm:
+            bound = "tensor"
+    traffic = TRAFFIC_PER_LAUNCH.get(name) if rows == CONFIGS[name]["rows"] else None
+    if bound == "tensor":
+        roofline = {"bound": "tensor", "achieved": tensor["executed_tflops"], "peak": tensor["peak_tflops"], "unit": "TFLOP/s",
+                    "frac": tensor["frac_executed"], "traffic": traffic,
+                    "peak_source": tensor["peak_source"], "kernel_ms": kern_ms,
+                    "note": "achieved = tensor-pipe flops the kernel executes (split terms x K steps incl. block padding); "
+                            "algorithmic 2*K flop/output figures are in `tensor` and `fp32`",
+                    "hbm": {"achieved": achieved_gbs, "peak": env.hbm_peak, "frac": achieved_gbs / env.hbm_peak}}
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": env.hbm_peak, "unit": "GB/s",
+                    "frac": achieved_gbs / env.hbm_peak, "traffic": traffic, "peak_source": env.peak_src, "kernel_ms": kern_ms}
+    roofline["tensor"] = tensor
+    roofline["fp32"] = {"achieved_tflops": achieved_tf, "peak_nominal_tflops": FP32_NOMINAL_TFLOPS,
+                        "frac_nominal": achieved_tf / FP32_NOMINAL_TFLOPS,
+                        "peak_ffma_microbench_tflops": env.ffma_tflops,
+                        "frac_of_microbench": achieved_tf / env.ffma_tflops if env.ffma_tflops else None,
+                        "note": "algorithmic 2*K flop/output against the CUDA-core FP32 peak; > 1 means the tensor path "
+                                "beat the FP32 roofline" if tensor_path else "direct-form FFMA kernel"}
+    roofline["shape_roofline"] = {"t_ms": t_roof * 1e3, "gsamples": outs / t_roof / 1e9, "frac": (t_roof * 1e3) / ms,
+                                  "note": "BASELINE.md per-shape roofline: max(bytes/measured HBM, 2*K flops/nominal FP32)"}
+    rec = {"workload": cfg["desc"], "rows_per_gpu": rows, "steps": steps, "ms_per_step": ms_max, "value": value, "unit": UNIT,
+           "roofline": roofline, "clocks": clocks, "clock_remeasured": remeasured,
+           "gpu_launches": int(launches), "tensor_core_launches": int(tc_launches),
+           "arithmetic": ("f32 in/out; " + tensor["split"]) if tensor else "f32 FFMA (CUDA cores)",
+           "l2": config_dict(name, cfg, rows, env.world)["l2"]}
+    if want_parity and cfg["op"] != "ew":
+        yd = y if not isinstance(y, np.ndarray) else torch.from_numpy(y)
+        try:
+            rec["parity"] = parity_check(cfg, taps, xs[last], yd)
+        except Exception as e:                              # the checker must never take the measurement down
+            rec["parity"] = {"error": repr(e)}
+    kept = (xs[last], y, taps, ctx) if keep else None
+    if not keep:
+        del xs, outs_buf, y
+        torch.cuda.empty_cache()
+    return rec, kept
+
+
+# ---- e2e: host arrays through the C ABI -------------------------------------------------------------------------------
+def host_call(env, cfg, taps, hctx_handle, xp, yp, rows, mg=None):
+    """The reference-facing call on host arrays for this config (lib.rs:515-531 and the scir-signal routes)."""
+    lib, L = env.L.lib(), env.L
+    n, n_out = cfg["n"], out_len(cfg)
+    fpp = C.POINTER(C.c_float)
+    tp = taps.ctypes.data_as(fpp)
+    if cfg["op"] in ("fir", "lfilter"):
+        order = L.TAPS_SCIR if cfg["op"] == "fir" else L.TAPS_LFILTER
+        if mg is not None:
+            return "scir_b200_mg_fir1d_batched_f32_host", lambda: lib.scir_b200_mg_fir1d_batched_f32_host(
+                mg, xp, n, tp, taps.size, order, yp, n_out, rows, n)
+        return "scir_b200_fir1d_batched_f32_host", lambda: lib.scir_b200_fir1d_batched_f32_host(
+            hctx_handle, xp, n, tp, taps.size, order, yp, n_out, rows, n)
+    if cfg["op"] == "resample":
+        if mg is not None:
+            return "scir_b200_mg_resample_poly_f32_host", lambda: lib.scir_b200_mg_resample_poly_f32_host(
+                mg, tp, taps.size, cfg["up"], cfg["down"], xp, n, rows, n, yp, n_out)
+        return "scir_b200_resample_poly_f32_host", lambda: lib.scir_b200_resample_poly_f32_host(
+            hctx_handle, tp, taps.size, cfg["up"], cfg["down"], xp, n, rows, n, yp, n_out)
+    if mg is not None:
+        return "scir_b200_mg_filtfilt_fir_f32_host", lambda: lib.scir_b200_mg_filtfilt_fir_f32_host(
+            mg, tp, taps.size, L.PAD_ODD, -1, xp, n, yp, n_out, rows, n)
+    return "scir_b200_filtfilt_fir_f32_host", lambda: lib.scir_b200_filtfilt_fir_f32_host(
+        hctx_handle, tp, taps.size, L.PAD_ODD, -1, xp, n, yp, n_out, rows, n)
+
+
+def measure_e2e(env, cfg, rows, steps, kept):
+    torch, lib, L = env.torch, env.L.lib(), env.L
+    x_dev, y_dev, taps, _ = kept
+    n, n_out = cfg["n"], out_len(cfg)
+    outs, _, _ = algorithmic(cfg, rows)
+    in_bytes, out_bytes = rows * n * 4, rows * n_out * 4
+    hx, hy = C.c_void_p(), C.c_void_p()
+    rc1, rc2 = lib.scir_b200_host_alloc(in_bytes, C.byref(hx)), lib.scir_b200_host_alloc(out_bytes, C.byref(hy))
+    ok_all = env.min_over_ranks(1.0 if (rc1 == 0 and rc2 == 0) else 0.0)        # every rank takes the same branch
+    if ok_all < 1.0:
+        e2e = {"value": None, "unit": UNIT, "error": L.last_error() or "pinned host allocation failed on another rank"}
+        if hx:
+            lib.scir_b200_host_free(hx)
+        if hy:
+            lib.scir_b200_host_free(hy)
+        return e2e
+    fpp = C.POINTER(C.c_float)
+    ax = np.ctypeslib.as_array(C.cast(hx, fpp), shape=(rows, n))
+    ay = np.ctypeslib.as_array(C.cast(hy, fpp), shape=(rows, n_out))
+    ax[:] = x_dev.cpu().numpy()
+    hctx = env.gpu.Context(env.local_rank)
+    for key, val in env.opts.items():
+        hctx.set_option(key, val)
+    yd = y_dev if not isinstance(y_dev, np.ndarray) else torch.from_numpy(y_dev)
+    y_head = yd[:2].cpu().numpy()
+    e_steps = max(3, min(steps, 10))
+
+    def timed(call, count, warm=2):
+        rc = 0
+        for _ in range(warm):
+            rc |= call()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(count):
+            rc |= call()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / count
+        return env.max_over_ranks(dt), rc
+
+    api, call = host_call(env, cfg, taps, hctx.handle, C.cast(hx, fpp), C.cast(hy, fpp), rows)
+    dt, rc = timed(call, e_steps)
+    ok = bool(rc == 0 and np.allclose(ay[:2], y_head, atol=1e-6))
+    e2e = {"value": outs * env.world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+           "d2h_bytes_per_step": out_bytes, "ms_per_step": dt * 1e3, "steps": e_steps,
+           "matches_device_path": ok, "gbs_each_way_per_gpu": in_bytes / dt / 1e9,
+           "api": api + " (pinned host buffers; H2D, kernels and D2H inside the timed region)"}
+    if rc != 0:
+        e2e["error"] = L.last_error()
+
+    # ---- the same call on PAGEABLE arrays: what a Rust Vec / ndarray::Array2 / numpy array is (lib.rs:1042-1044) ----
+    try:
+        px = np.empty((rows, n), np.float32)
+        py = np.empty((rows, n_out), np.float32)
+        px[:] = ax
+        py[:] = 0
+        pin = C.c_int(-1)
+        lib.scir_b200_host_is_pinned(px.ctypes.data_as(C.c_void_p), px.nbytes, C.byref(pin))
+        _, pcall = host_call(env, cfg, taps, hctx.handle, px.ctypes.data_as(fpp), py.ctypes.data_as(fpp), rows)
+        p_steps = max(2, min(steps, 5))
+        s0 = hctx.get_option("host_staged_calls")
+        dtp, rcp = timed(pcall, p_steps, warm=1)
+        okp = bool(rcp == 0 and np.allclose(py[:2], y_head, atol=1e-6) and np.array_equal(py[-1], ay[-1]))
+        e2e["pageable"] = {"value": outs * env.world / dtp / 1e9, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": p_steps,
+                           "vs_pinned": dt / dtp, "matches_device_path": okp, "input_is_pinned": int(pin.value),
+                           "route": "ctx pinned ring + copy threads" if hctx.get_option("host_staged_calls") > s0 else
+                                    ("cudaHostRegister per call" if hctx.get_option("host_registered_calls") > 0 else
+                                     "cudaMemcpyAsync on pageable memory"),
+                           "copy_threads": hctx.get_option("host_copy_threads") or "auto"}
+        if rcp != 0:
+            e2e["pageable"]["error"] = L.last_error()
+        del px, py
+    except MemoryError as e:
+        e2e["pageable"] = {"error": repr(e)}
+
+    # ---- ceiling: plain pinned copies of a block of the same traffic, every rank at once ------------------------------
+    try:
+        h2d, d2h, dup = C.c_double(), C.c_double(), C.c_double()
+        env.barrier()
+        rcc = lib.scir_b200_microbench_pcie(hctx.handle, 1 << 30, 3, C.byref(h2d), C.byref(d2h), C.byref(dup))
+        if rcc == 0:
+            dup_min = env.min_over_ranks(dup.value)
+            dup_sum = env.sum_over_ranks(dup.value)
+            e2e["ceiling"] = {"h2d_alone_gbs": h2d.value, "d2h_alone_gbs": d2h.value, "duplex_each_way_gbs": dup.value,
+                              "duplex_each_way_gbs_min_over_ranks": dup_min, "duplex_each_way_gbs_sum_over_ranks": dup_sum,
+                              "note": "cudaMemcpyAsync of 1 GiB pinned buffers, both directions at once, all ranks concurrently "
+                                      "(rank 0's figures; min / sum over ranks beside them)",
+                              "frac_of_ceiling": (in_bytes / dt / 1e9) / dup_min if dup_min else None}
+            e2e["ceiling_gbs"] = dup_min
+    except Exception as e:
+        e2e["ceiling"] = {"error": repr(e)}
+
+    # ---- N > 1: the in-process front end north_star (d) describes -- rank 0 drives all N GPUs, the others wait ------
+    if env.world > 1:
+        env.barrier()
+        mg_rec = None
+        if env.rank == 0:
+            try:
+                devs = (C.c_int * env.world)(*range(env.world))
+                mg = C.c_void_p()
+                rcm = lib.scir_b200_mg_create(devs, env.world, C.byref(mg))
+                if rcm == 0:
+                    _, mcall = host_call(env, cfg, taps, None, C.cast(hx, fpp), C.cast(hy, fpp), rows, mg=mg)
+                    ay[:] = 0
+                    for _ in range(2):
+                        rcm |= mcall()
+                    t0 = time.perf_counter()
+                    for _ in range(e_steps):
+                        rcm |= mcall()
+                    dtm = (time.perf_counter() - t0) / e_steps
+                    okm = bool(rcm == 0 and np.allclose(ay[:2], y_head, atol=1e-6))
+                    mg_rec = {"value": outs / dtm / 1e9, "unit": UNIT, "ms_per_step": dtm * 1e3, "steps": e_steps,
+                              "devices": env.world, "rows_total": rows, "rows_per_gpu": rows // env.world,
+                              "matches_device_path": okm,
+                              "api": "scir_b200_mg_*_host: ONE host call, rows of the FIXED problem (this config's rows) sharded "
+                                     "over the N devices, one stream + host thread per device (pinned arrays)"}
+                    lib.scir_b200_mg_destroy(mg)
+                if rcm != 0:
+                    mg_rec = {"error": L.last_error()}
+            except Exception as e:
+                mg_rec = {"error": repr(e)}
+        env.barrier()
+        e2e["mg"] = mg_rec
+    lib.scir_b200_host_free(hx)
+    lib.scir_b200_host_free(hy)
+    hctx.close()
+    return e2e
+
+
+# ---- CPU reference arm ---------------------------------------------------------------------------------------------
+def cpu_cfg(cfg, taps):
+    """The reference's CPU path for a config, as the oracle port's FIR loop: (effective cfg, taps, passes)."""
+    if cfg["op"] == "resample":
+        # the reference has no general resampler; its CPU path for this route is the same MAC loop per output over
+        # the polyphase taps: time the FIR port at the per-output tap count
+        eff = dict(cfg, k=cfg["k"] // cfg["up"], op="lfilter")
+        return eff, taps[: eff["k"]], 1
+    return cfg, taps, (2 if cfg["op"] == "filtfilt" else 1)
+
+
+_CPU_X = {}
+
+
+def cpu_time_rows(cfg, taps, threads, rows, passes):
+    """Seconds for `rows` rows of the oracle port of gpu/lib.rs:1134-1152 on `threads` threads."""
+    from oracle import oracle as O
+    key = (rows, cfg["n"])
+    if key not in _CPU_X:
+        _CPU_X.clear()
+        _CPU_X[key] = (np.random.RandomState(42).rand(rows, cfg["n"]).astype(np.float32) * 2 - 1)
+    x = _CPU_X[key]
     kern_taps = taps if cfg["op"] == "fir" else taps[::-1].copy()    # kernel order = reversed lfilter order
     t0 = time.perf_counter()
-    O.fir1d_batched_f32_mt(x, kern_taps, threads)
-    dt = time.perf_counter() - t0
-    reps = 1
-    if cfg["op"] == "filtfilt":
-        reps = 2
-    want_rows = int(max(rows, min(rows * budget_s / max(dt * reps, 1e-6), 4096)))
-    want_rows = max(threads, (want_rows // threads) * threads)
-    if want_rows != rows:
-        x = (rng.rand(want_rows, n).astype(np.float32) * 2 - 1)
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    for _ in range(passes):
         O.fir1d_batched_f32_mt(x, kern_taps, threads)
-    dt = time.perf_counter() - t0
-    return want_rows * n / dt / 1e9, want_rows, dt
+    return time.perf_counter() - t0
 
 
-def reference_arm(args, cfg, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; Rust is not buildable here)."""
+def cpu_reference_rate(cfg, taps, threads, budget_s):
+    """Times the oracle port over a bounded row sample sized for ~budget_s.  Returns (Gsamples/s, rows, seconds)."""
+    eff, ctaps, passes = cpu_cfg(cfg, taps)
+    rows = max(1, threads)
+    dt = cpu_time_rows(eff, ctaps, threads, rows, passes)
+    want = int(max(rows, min(rows * budget_s / max(dt, 1e-6), 4096)))
+    want = max(threads, (want // threads) * threads)
+    if want != rows:
+        rows = want
+        dt = cpu_time_rows(eff, ctaps, threads, rows, passes)
+    return rows * cfg["n"] / dt / 1e9, rows, dt
+
+
+def reference_arm(args, name, cfg, rank, world):
+    """--impl reference: the reference's CPU path (oracle port; Rust is not buildable here).  Exactly --steps steps,
+    each one bounded sample of the workload (the row count is fixed after a calibration pass)."""
     if rank != 0:
         return
     taps = make_taps(cfg)
     threads = os.cpu_count() or 1
-    if cfg["op"] == "resample":
-        # the reference has no general resampler; its CPU path for this route is the same MAC loop
-        # per output over the polyphase taps: time the FIR port at the per-output tap count
-        eff = dict(cfg, k=cfg["k"] // cfg["up"], op="lfilter")
-        taps = taps[: eff["k"]]
-    else:
-        eff = cfg
-    vals = []
-    per_step_budget = 2.0
+    eff, ctaps, passes = cpu_cfg(cfg, taps)
+    per_step = min(2.0, 90.0 / max(args.steps + args.warmup, 1))
+    dt0 = cpu_time_rows(eff, ctaps, threads, threads, passes)             # calibration (untimed)
+    rows = int(max(threads, min(threads * per_step / max(dt0, 1e-6), 4096)))
+    rows = max(threads, (rows // threads) * threads)
     for _ in range(args.warmup):
-        cpu_reference_rate(eff, taps, threads, 0.3)
-    t_all = time.perf_counter()
-    sample = None
+        cpu_time_rows(eff, ctaps, threads, rows, passes)
+    ratio = 1.0       # outputs timed = rows * n at the config's per-output tap count (see cpu_cfg)
+    vals, dts = [], []
     for _ in range(args.steps):
-        g, rows, dt = cpu_reference_rate(eff, taps, threads, per_step_budget)
-        vals.append(g)
-        sample = f"{rows} rows x {cfg['n']} samples per step ({dt:.2f} s), extrapolated linearly over rows"
-        if time.perf_counter() - t_all > 150:
-            break
+        dt = cpu_time_rows(eff, ctaps, threads, rows, passes)
+        dts.append(dt)
+        vals.append(rows * cfg["n"] * ratio / dt / 1e9)
     v = float(np.median(vals))
+    # what the reference actually ships is single-threaded (no rayon anywhere): state that figure too
+    rows1 = max(1, int(rows / threads / 2) or 1)
+    dt1 = cpu_time_rows(eff, ctaps, 1, rows1, passes)
+    v1 = rows1 * cfg["n"] * ratio / dt1 / 1e9
     outs, _, _ = algorithmic(cfg, cfg["rows"])
+    sample = (f"{rows} of {cfg['rows']} rows x {cfg['n']} samples per step ({float(np.median(dts)):.2f} s), rows independent: "
+              "extrapolated linearly")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": outs / (v * 1e9) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "config": args.config, "note": "CPU port of gpu/lib.rs:1134-1152, row-parallel"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": config_dict(name, cfg, cfg["rows"], world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread": {"value": v1, "cores": 1, "sample": f"{rows1} rows ({dt1:.2f} s)",
+                                           "note": "the reference loop as shipped is single-threaded (gpu/lib.rs:1134-1152)"},
+                         "note": "CPU port of gpu/lib.rs:1134-1152 (oracle/fir_oracle.c), row-parallel over all host threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -235,238 +694,103 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="only the headline config (skip `configs` and `strong`)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="ctx option for A/B runs, e.g. long_tap_path=2 toeplitz_terms=3")
     args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
+    name = args.config
+    cfg = dict(CONFIGS[name])
     if args.rows:
         cfg["rows"] = args.rows
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        reference_arm(args, cfg, rank, world)
+        reference_arm(args, name, cfg, rank, world)
         return
 
-    import torch
-    import torch.distributed as dist
-    from scir_b200 import _lib as L
-    from scir_b200 import dist as sdist
-    from scir_b200 import gpu, signal
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    rows, n = cfg["rows"], cfg["n"]
-    taps = make_taps(cfg)
-    # weak scaling: every rank owns `rows` channels of a (rows*world)-channel problem
-    r0, r1 = sdist.shard_rows(rows * world, world, rank)
+    env = Env(args)
+    torch = env.torch
+    rows = cfg["rows"]
+    r0, r1 = env.sdist.shard_rows(rows * world, world, rank)     # weak scaling: every rank owns `rows` channels
     assert r1 - r0 == rows
-    g = torch.Generator(device=dev).manual_seed(42 + rank)
-    x = torch.rand((rows, n), device=dev, generator=g) * 2 - 1
-    out = torch.empty_like(x) if cfg["op"] in ("fir", "lfilter", "ew") else None
-    ctx = gpu.torch_context(x)
-    if args.variant:
-        ctx.set_option("variant", args.variant)
-    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
-    for key, val in opts.items():
-        ctx.set_option(key, val)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        y = run_step(cfg, signal, gpu, x, taps, out)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.sample()
-    sampler.start()
-    l0 = ctx.launch_count()
-    tc0 = ctx.get_option("toeplitz_launches")
-    fx0 = ctx.get_option("fixup_launches")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        y = run_step(cfg, signal, gpu, x, taps, out)
-    e1.record()
-    torch.cuda.synchronize()
-    launches = ctx.launch_count() - l0
-    ms = e0.elapsed_time(e1) / args.steps
-    barrier()
-    sampler.sample()
-    clocks = sampler.result()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    outs, abytes, aflops = algorithmic(cfg, rows)
-    value = outs * world / (ms_max * 1e-3) / 1e9
-
-    # ---- per-kernel launch time for the roofline (events on the launching stream) -------------------
-    hbm_peak, peak_src, peaks = measured_peaks()
+    # the FP32 denominator measured on this box (for roofline.fp32)
+    probe = torch.empty(4, device=env.dev)
     ffma = C.c_double(0.0)
-    L.lib().scir_b200_microbench_ffma(ctx.handle, 2000, C.byref(ffma))
-    tc_launches = ctx.get_option("toeplitz_launches") - tc0
-    tensor_path = tc_launches > 0
-    # dominant-kernel launches per step (filtfilt: two).  Every FIR launch is followed by its non-finite
-    # fix-up kernel (~3 us with finite data), counted in gpu_launches but not a "dominant kernel".
-    n_kern = max((launches - (ctx.get_option("fixup_launches") - fx0)) / args.steps, 1)
-    kern_ms = ms / n_kern
-    achieved_gbs = abytes / (ms * 1e-3) / 1e9
-    achieved_tf = aflops / (ms * 1e-3) / 1e12
-    t_hbm = abytes / (hbm_peak * 1e9)
-    t_fp32 = aflops / (FP32_NOMINAL_TFLOPS * 1e12)
-    t_roof = max(t_hbm, t_fp32)
-    tensor = None
-    bound = "hbm"
-    if tensor_path:
-        # what the tcgen05 Toeplitz kernel executes: per 128 x 128 output tile, `terms` M128 N128 K16 MMAs for
-        # every K step of every Toeplitz block that meets a non-zero tap (fir_toeplitz.cu: issue_tile)
-        terms = opts.get("toeplitz_terms", 3)
-        k = cfg["k"]
-        passes = 1
-        if cfg["op"] == "filtfilt":
-            if tc_launches // args.steps == 1:             # padded filtfilt fused into one zero-phase pass of 2K-1 taps
-                k = 2 * k - 1
-            else:
-                passes = 2
-        pmax = (k - 1 + 127) // 128
-        ksteps = sum(8 - (max(0, 128 * pb - (k - 1)) >> 4) for pb in range(pmax + 1))
-        exec_flop_per_out = terms * ksteps * (2.0 * 128 * 128 * 16) / (128 * 128)
-        exec_tf = outs * passes * exec_flop_per_out / (ms * 1e-3) / 1e12
-        tc_peak = float(peaks.get("bf16_tflops", 2250.0))
-        t_tensor = outs * passes * exec_flop_per_out / (tc_peak * 1e12)
-        tensor = {"split": "fp16x%d block-scaled, fp32 accumulate in TMEM" % terms if not opts.get("toeplitz_split") else
-                           "bf16x%d, fp32 accumulate in TMEM" % terms,
-                  "executed_tflops": exec_tf, "peak_tflops": tc_peak,
-                  "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in peaks else "nominal 2250",
-                  "peak_sustained_tflops": peaks.get("bf16_tflops_sustained"),
-                  "frac_executed": exec_tf / tc_peak,
-                  "algorithmic_tflops": achieved_tf, "frac_algorithmic_x_terms": achieved_tf * terms / tc_peak,
-                  "mma_per_tile": terms * ksteps}
-        if t_tensor > t_hbm:
-            bound = "tensor"
-    if bound == "tensor":
-        roofline = {"bound": "tensor", "achieved": tensor["executed_tflops"], "peak": tensor["peak_tflops"], "unit": "TFLOP/s",
-                    "frac": tensor["frac_executed"], "traffic": TRAFFIC_PER_LAUNCH.get(args.config),
-                    "peak_source": tensor["peak_source"], "kernel_ms": kern_ms,
-                    "note": "achieved = tensor-pipe flops the kernel executes (split terms x K steps incl. block padding); "
-                            "algorithmic 2*K flop/output figures are in `tensor` and `fp32`",
-                    "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "frac": achieved_gbs / hbm_peak}}
-    else:
-        roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                    "traffic": TRAFFIC_PER_LAUNCH.get(args.config), "peak_source": peak_src, "kernel_ms": kern_ms}
-    roofline["tensor"] = tensor
-    roofline["fp32"] = {"achieved_tflops": achieved_tf, "peak_nominal_tflops": FP32_NOMINAL_TFLOPS,
-                        "frac_nominal": achieved_tf / FP32_NOMINAL_TFLOPS, "peak_ffma_microbench_tflops": ffma.value,
-                        "frac_of_microbench": achieved_tf / ffma.value if ffma.value else None,
-                        "note": "algorithmic 2*K flop/output against the CUDA-core FP32 peak; > 1 means the tensor path "
-                                "beat the FP32 roofline" if tensor_path else "direct-form FFMA kernel"}
-    roofline["shape_roofline"] = {"t_ms": t_roof * 1e3, "gsamples": outs / t_roof / 1e9, "frac": (t_roof * 1e3) / ms,
-                                  "note": "BASELINE.md per-shape roofline: max(bytes/measured HBM, 2*K flops/nominal FP32)"}
+    env.L.lib().scir_b200_microbench_ffma(env.gpu.torch_context(probe).handle, 2000, C.byref(ffma))
+    env.ffma_tflops = ffma.value
 
-    # ---- e2e: host arrays through the C ABI (pinned buffers, H2D + kernel + D2H timed) ------------------
-    e2e = None
-    if not args.no_e2e and cfg["op"] != "ew":
-        lib = L.lib()
-        if cfg["op"] == "resample":
-            n_out = -(-n * cfg["up"] // cfg["down"])
-        else:
-            n_out = n
-        in_bytes, out_bytes = rows * n * 4, rows * n_out * 4
-        hx, hy = C.c_void_p(), C.c_void_p()
-        rc1, rc2 = lib.scir_b200_host_alloc(in_bytes, C.byref(hx)), lib.scir_b200_host_alloc(out_bytes, C.byref(hy))
-        alloc_ok = torch.tensor([1 if (rc1 == 0 and rc2 == 0) else 0], device=dev, dtype=torch.int32)
-        if world > 1:                                      # every rank takes the same branch (barriers inside)
-            dist.all_reduce(alloc_ok, op=dist.ReduceOp.MIN)
-        if int(alloc_ok.item()) == 1:
-            ax = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=(rows, n))
-            ay = np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_float)), shape=(rows, n_out))
-            ax[:] = x.cpu().numpy()
-            hctx = gpu.Context(local_rank)
-            for key, val in opts.items():
-                hctx.set_option(key, val)
-            fpp = C.POINTER(C.c_float)
-            tp = taps.ctypes.data_as(fpp)
-            xp, yp = C.cast(hx, fpp), C.cast(hy, fpp)
-            if cfg["op"] in ("fir", "lfilter"):
-                order = L.TAPS_SCIR if cfg["op"] == "fir" else L.TAPS_LFILTER
-                api = "scir_b200_fir1d_batched_f32_host"
-                call = lambda: lib.scir_b200_fir1d_batched_f32_host(hctx.handle, xp, n, tp, taps.size, order, yp, n_out, rows, n)
-            elif cfg["op"] == "resample":
-                api = "scir_b200_resample_poly_f32_host"
-                call = lambda: lib.scir_b200_resample_poly_f32_host(hctx.handle, tp, taps.size, cfg["up"], cfg["down"], xp, n,
-                                                                    rows, n, yp, n_out)
-            else:
-                api = "scir_b200_filtfilt_fir_f32_host"
-                call = lambda: lib.scir_b200_filtfilt_fir_f32_host(hctx.handle, tp, taps.size, L.PAD_ODD, -1, xp, n, yp, n_out,
-                                                                   rows, n)
-            e_steps = max(3, min(args.steps, 10))
-            rc = 0
-            for _ in range(2):
-                rc |= call()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(e_steps):
-                rc |= call()
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / e_steps
-            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            yd = y if not isinstance(y, np.ndarray) else torch.from_numpy(y)
-            ok = bool(rc == 0 and np.allclose(ay[:2], yd[:2].cpu().numpy(), atol=1e-6))
-            e2e = {"value": outs * world / float(tt.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-                   "d2h_bytes_per_step": out_bytes, "ms_per_step": float(tt.item()) * 1e3, "steps": e_steps,
-                   "matches_device_path": ok, "api": api + " (pinned host buffers; H2D, kernels and D2H inside the timed region)"}
-            if rc != 0:
-                e2e["error"] = L.last_error()
-        else:
-            e2e = {"value": None, "unit": UNIT, "error": L.last_error() or "pinned host allocation failed on another rank"}
-        if hx:
-            lib.scir_b200_host_free(hx)
-        if hy:
-            lib.scir_b200_host_free(hy)
+    want_e2e = not args.no_e2e and cfg["op"] != "ew"
+    head, kept = measure_config(env, name, cfg, rows, args.steps, args.warmup, keep=want_e2e)
+    e2e = measure_e2e(env, cfg, rows, args.steps, kept) if want_e2e else None
+    del kept
+    torch.cuda.empty_cache()
+
+    # ---- every BASELINE config, same rules (device-resident) --------------------------------------------------
+    sweep, strong = None, None
+    if not args.no_sweep and not args.rows and name in BASELINE_CONFIGS:
+        sweep = {}
+        for cn in BASELINE_CONFIGS:
+            if cn == name:
+                sweep[cn] = {k: v for k, v in head.items()}
+                continue
+            c = CONFIGS[cn]
+            outs_c, abytes_c, _ = algorithmic(c, c["rows"])
+            steps_c = args.steps if abytes_c > 3e8 else max(args.steps, 200)     # short configs: enough steps for the clock sampler
+            try:
+                sweep[cn], _ = measure_config(env, cn, c, c["rows"], steps_c, args.warmup)
+            except Exception as e:
+                sweep[cn] = {"error": repr(e)}
+        # ---- the BASELINE shapes as FIXED problems split over N GPUs (strong scaling) ------------------------------
+        if world > 1:
+            strong = {}
+            for cn in STRONG_CONFIGS:
+                c = CONFIGS[cn]
+                if c["rows"] % world:
+                    continue
+                try:
+                    rec, _ = measure_config(env, cn, c, c["rows"] // world, args.steps, args.warmup)
+                    t1 = sweep[cn]["ms_per_step"]                               # the whole problem on ONE GPU, this run (max over ranks)
+                    outs_total, _, _ = algorithmic(c, c["rows"])
+                    strong[cn] = {"workload": c["desc"] + f" split over {world} GPUs", "rows_per_gpu": c["rows"] // world,
+                                  "ms": rec["ms_per_step"], "value": outs_total / (rec["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
+                                  "one_gpu_ms": t1, "speedup_vs_n1": t1 / rec["ms_per_step"],
+                                  "efficiency_vs_n1": t1 / rec["ms_per_step"] / world,
+                                  "roofline": {k: rec["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")},
+                                  "clocks": rec["clocks"], "parity": rec.get("parity"), "gpu_launches": rec["gpu_launches"]}
+                except Exception as e:
+                    strong[cn] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and cfg["op"] != "ew":
-        eff, ctaps = cfg, taps
-        if cfg["op"] == "resample":
-            eff = dict(cfg, k=cfg["k"] // cfg["up"], op="lfilter")
-            ctaps = taps[: eff["k"]]
-        v1, rows1, dt1 = cpu_reference_rate(eff, ctaps, 1, 8.0)
+        taps = make_taps(cfg)
+        v1, rows1, dt1 = cpu_reference_rate(cfg, taps, 1, 8.0)
         threads = os.cpu_count() or 1
-        vn, rowsn, dtn = cpu_reference_rate(eff, ctaps, threads, 8.0)
+        vn, rowsn, dtn = cpu_reference_rate(cfg, taps, threads, 8.0)
         cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{rows1} of {rows} rows x {n} samples ({dt1:.1f} s), rows independent: extrapolated linearly",
+               "sample": f"{rows1} of {rows} rows x {cfg['n']} samples ({dt1:.1f} s), rows independent: extrapolated linearly",
                "all_cores": {"value": vn, "cores": threads, "sample": f"{rowsn} rows ({dtn:.1f} s)"}}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "config": args.config, "rows_per_gpu": rows, "n": n, "taps": cfg["k"],
-                       "global_rows": rows * world, "sharding": f"rows x{world}, no collective",
-                       "l2": "inputs larger than L2 (per-step working set >> 126 MB)" if abytes > 3e8 else
-                             "working set fits L2 (latency/plumbing config)",
-                       "variant": args.variant, "options": opts,
-                       "tensor_core_launches": int(tc_launches),
-                       "arithmetic": ("f32 in/out; " + tensor["split"]) if tensor else "f32 FFMA (CUDA cores)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "config": config_dict(name, cfg, rows, world),
+            "gpu": {"variant": args.variant, "options": env.opts, "tensor_core_launches": head["tensor_core_launches"],
+                    "arithmetic": head["arithmetic"]},
+            "roofline": head["roofline"], "parity": head.get("parity"), "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "configs": sweep, "strong": strong,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        env.dist.destroy_process_group()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed

@@ -1,0 +1,131 @@
+//! `scir_signal::gpu` -- GPU-forwarded FIR routes (feature `gpu`), the replacement for
+//! crates/scir-signal/src/lib.rs:365-375 of SoftOboros/scir.  Mount with
+//!
+//! ```ignore
+//! #[cfg(feature = "gpu")]
+//! #[path = "gpu.rs"]
+//! pub mod gpu;
+//! ```
+//!
+//! `fir1d_batched_f32` keeps the reference's signature (sig/lib.rs:372).  The other functions are the FIR routes
+//! north_star (c) maps onto the same kernels -- `lfilter` with `a = [1]`, `upfirdn` / `resample_poly`, FIR `filtfilt`
+//! -- with SciPy's semantics (the reference's own `resample_poly` / `filtfilt`, sig/lib.rs:278-362, are f64 and
+//! CPU-only; their f64 twins are `resample_poly_f64` / `filtfilt_fir_f64` below).
+use ndarray::{Array1, Array2};
+use scir_gpu::{fir1d_batched_f32_auto, Device, GpuError};
+
+/// Batched FIR for f32 with device selection (sig/lib.rs:372-374).
+pub fn fir1d_batched_f32(x: &Array2<f32>, taps: &Array1<f32>, device: Device) -> Array2<f32> {
+    fir1d_batched_f32_auto(x, taps, device)
+}
+
+#[cfg(feature = "cuda")]
+mod routes {
+    use super::*;
+    use scir_gpu::ffi;
+    use scir_gpu::with_default_context;
+    use std::ffi::CStr;
+
+    fn check(rc: std::os::raw::c_int) -> Result<(), GpuError> {
+        if rc == ffi::SCIR_B200_OK {
+            return Ok(());
+        }
+        if rc == ffi::SCIR_B200_ERR_SHAPE {
+            return Err(GpuError::ShapeMismatch);
+        }
+        let msg = unsafe { CStr::from_ptr(ffi::scir_b200_last_error()) }.to_string_lossy().into_owned();
+        Err(GpuError::BackendUnavailable(format!("scir_b200 error {rc}: {msg}")))
+    }
+
+    fn ld(n: usize) -> i64 {
+        if n > 0 { n as i64 } else { 1 }
+    }
+
+    /// Padding of [`filtfilt_fir`]: SciPy's `padtype` plus the reference's own unpadded structure.
+    #[derive(Clone, Copy, Debug, PartialEq, Eq)]
+    pub enum PadType {
+        /// zero-state forward, reverse, zero-state forward, reverse (sig/lib.rs:278-291)
+        ZeroState,
+        /// SciPy default
+        Odd,
+        /// even extension
+        Even,
+        /// constant extension
+        Constant,
+        /// SciPy `padtype=None`
+        NoPad,
+    }
+
+    impl PadType {
+        fn code(self) -> std::os::raw::c_int {
+            match self {
+                PadType::ZeroState => ffi::SCIR_B200_PAD_ZERO_STATE,
+                PadType::Odd => ffi::SCIR_B200_PAD_ODD,
+                PadType::Even => ffi::SCIR_B200_PAD_EVEN,
+                PadType::Constant => ffi::SCIR_B200_PAD_CONSTANT,
+                PadType::NoPad => ffi::SCIR_B200_PAD_SCIPY_NONE,
+            }
+        }
+    }
+
+    /// `lfilter(b, [1], x)` along the rows: `y[r,i] = sum_d b[d] * x[r,i-d]` (SciPy tap order -- the reverse of
+    /// `fir1d_batched_f32`'s).
+    pub fn lfilter_fir(b: &Array1<f32>, x: &Array2<f32>) -> Result<Array2<f32>, GpuError> {
+        let (rows, n) = x.dim();
+        let xs = x.as_standard_layout();
+        let bs = b.as_standard_layout();
+        let mut out = vec![0.0f32; rows * n];
+        with_default_context(|ctx| {
+            check(unsafe {
+                ffi::scir_b200_fir1d_batched_f32_host(
+                    ctx.as_ptr(), xs.as_ptr(), ld(n), bs.as_ptr(), bs.len() as i64, ffi::SCIR_B200_TAPS_LFILTER,
+                    out.as_mut_ptr(), ld(n), rows as i64, n as i64,
+                )
+            })
+        })?;
+        Array2::from_shape_vec((rows, n), out).map_err(|_| GpuError::ShapeMismatch)
+    }
+
+    /// `resample_poly(x, up, down, window=h)` along the rows, `padtype='constant'` (SciPy
+    /// `_signaltools.py:3865-3957`); output is `(rows, ceil(n*up/down))`.
+    pub fn resample_poly(x: &Array2<f32>, up: usize, down: usize, window: &Array1<f32>) -> Result<Array2<f32>, GpuError> {
+        let (rows, n) = x.dim();
+        let mut plan = ffi::ScirB200ResamplePlan::default();
+        check(unsafe { ffi::scir_b200_resample_poly_plan(n as i64, window.len() as i64, up as i64, down as i64, &mut plan) })?;
+        let n_out = if plan.up == 1 && plan.down == 1 { n } else { plan.n_out as usize };
+        let xs = x.as_standard_layout();
+        let ws = window.as_standard_layout();
+        let mut out = vec![0.0f32; rows * n_out];
+        with_default_context(|ctx| {
+            check(unsafe {
+                ffi::scir_b200_resample_poly_f32_host(
+                    ctx.as_ptr(), ws.as_ptr(), ws.len() as i64, up as i64, down as i64, xs.as_ptr(), ld(n), rows as i64,
+                    n as i64, out.as_mut_ptr(), ld(n_out),
+                )
+            })
+        })?;
+        Array2::from_shape_vec((rows, n_out), out).map_err(|_| GpuError::ShapeMismatch)
+    }
+
+    /// Zero-phase forward-backward filtering with an FIR numerator `b` (SciPy `filtfilt(b, [1], x, padtype, padlen)`,
+    /// `_signaltools.py:4745-4826`; `PadType::ZeroState` is the reference's structure).  `padlen = None`: 3 * len(b).
+    pub fn filtfilt_fir(b: &Array1<f32>, x: &Array2<f32>, pad: PadType, padlen: Option<usize>) -> Result<Array2<f32>, GpuError> {
+        let (rows, n) = x.dim();
+        let xs = x.as_standard_layout();
+        let bs = b.as_standard_layout();
+        let mut out = vec![0.0f32; rows * n];
+        let pl = padlen.map(|p| p as i64).unwrap_or(-1);
+        with_default_context(|ctx| {
+            check(unsafe {
+                ffi::scir_b200_filtfilt_fir_f32_host(
+                    ctx.as_ptr(), bs.as_ptr(), bs.len() as i64, pad.code(), pl, xs.as_ptr(), ld(n), out.as_mut_ptr(), ld(n),
+                    rows as i64, n as i64,
+                )
+            })
+        })?;
+        Array2::from_shape_vec((rows, n), out).map_err(|_| GpuError::ShapeMismatch)
+    }
+}
+
+#[cfg(feature = "cuda")]
+pub use routes::{filtfilt_fir, lfilter_fir, resample_poly, PadType};

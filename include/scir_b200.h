@@ -15,8 +15,11 @@
  *     (lib.rs:1040-1044).  `ld_*` is the row pitch in ELEMENTS (>= row length).  All sizes are
  *     64-bit (the reference truncated b*n to u32, lib.rs:1083).
  *   - `d_*` pointers are device pointers on the ctx's device; `h_*` / taps are host pointers.
- *     Taps are always passed from the host (<= SCIR_B200_MAX_TAPS floats) and travel to the kernels
- *     as launch parameters, so there is no global constant-memory state and ctxs are independent.
+ *     Taps are always passed from the host (<= SCIR_B200_MAX_TAPS floats).  The FP32 kernels receive them as
+ *     launch parameters, the tcgen05 kernel from a ctx-owned device buffer that is re-uploaded only when the
+ *     filter changes; either way there is no global constant-memory state and ctxs are independent.
+ *   - No entry point changes the calling thread's current CUDA device / context: the ctx's device is bound
+ *     for the duration of the call and the caller's context is restored on return.
  *   - Device-pointer entry points are asynchronous on the ctx's stream; the *_host entry points
  *     (H2D + kernels + D2H, what the reference-shaped Rust functions call) return when the
  *     output is complete in host memory.
@@ -46,7 +49,7 @@ extern "C" {
 #define SCIR_B200_ERR_SHAPE         -5   /* maps to GpuError::ShapeMismatch (lib.rs:62)             */
 #define SCIR_B200_ERR_UNSUPPORTED   -6   /* valid request this build cannot serve (e.g. k too big)  */
 
-#define SCIR_B200_MAX_TAPS        7936   /* taps ride in the 32 KiB kernel-parameter space          */
+#define SCIR_B200_MAX_TAPS        7936   /* the FP32 kernels' taps ride in the 32 KiB kernel-parameter space */
 
 /* Tap order for scir_b200_fir1d_batched_f32. */
 #define SCIR_B200_TAPS_SCIR          0   /* reference order: y[i] = sum_t taps[k-1-t] * x[i-t]  (lib.rs:1141-1148) */
@@ -90,6 +93,15 @@ SCIR_B200_API int scir_b200_memcpy_h2d(scir_b200_ctx *ctx, void *d_dst, const vo
 SCIR_B200_API int scir_b200_memcpy_d2h(scir_b200_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* sync */
 SCIR_B200_API int scir_b200_host_alloc(size_t bytes, void **h_ptr);      /* pinned host memory for the *_host paths */
 SCIR_B200_API int scir_b200_host_free(void *h_ptr);
+/* Pin (page-lock) memory the caller already owns -- a Rust Vec / ndarray / numpy buffer that is reused across calls --
+ * so the *_host entry points DMA it directly.  Unregister before freeing it.  Registering costs about as much as
+ * one pass over the bytes, so it pays for buffers that live longer than one call. */
+SCIR_B200_API int scir_b200_host_register(void *h_ptr, size_t bytes);
+SCIR_B200_API int scir_b200_host_unregister(void *h_ptr);
+/* *pinned = 1 if [h_ptr, h_ptr+bytes) is page-locked memory CUDA knows (host_alloc / host_register), else 0. */
+SCIR_B200_API int scir_b200_host_is_pinned(const void *h_ptr, size_t bytes, int *pinned);
+/* The calling thread's current CUDA device (what a default ctx should be created on in a multi-GPU process). */
+SCIR_B200_API int scir_b200_current_device(int *device);
 
 /* ---- the hot path: replaces fir1d_batched_f32_cuda + PTX entry (lib.rs:1036-1113, 727-811) ----
  * y[b,i] = sum_{t=0}^{min(i,k-1)} c[t] * x[b,i-t], zero initial state, same shape as x,
@@ -100,7 +112,10 @@ SCIR_B200_API int scir_b200_fir1d_batched_f32(scir_b200_ctx *ctx,
                                 float *d_y, int64_t ld_y,
                                 int64_t batch, int64_t n);
 /* Same with host arrays (what fir1d_batched_f32_auto(.., Device::Cuda) calls, lib.rs:515-531):
- * rows are streamed through the device in blocks, H2D / kernel / D2H overlapped. */
+ * rows are streamed through the device in blocks, H2D / kernel / D2H overlapped.  Pinned arrays
+ * (scir_b200_host_alloc / scir_b200_host_register) are DMA'd in place; pageable arrays -- a Rust Vec, an
+ * ndarray::Array2, a numpy buffer -- go through the ctx's pinned ring, filled and drained by its copy threads
+ * (ctx option "host_stage": 1 ring [default], 0 plain cudaMemcpyAsync, 2 register the spans for the call). */
 SCIR_B200_API int scir_b200_fir1d_batched_f32_host(scir_b200_ctx *ctx,
                                      const float *h_x, int64_t ld_x,
                                      const float *taps, int64_t k, int tap_order,
@@ -139,7 +154,7 @@ enum {
     SCIR_B200_EXT_ANTIREFLECT = 7, SCIR_B200_EXT_LINE = 8
 };
 /* resample_poly padtypes beyond the extension modes (_signaltools.py:3921-3957): a per-row statistic is removed
- * before and restored after a zero-padded upfirdn.  MEDIAN is not implemented on the device yet (UNSUPPORTED). */
+ * before and restored after a zero-padded upfirdn (the median is an exact per-row radix select on the device). */
 enum { SCIR_B200_PAD_STAT_MEAN = 16, SCIR_B200_PAD_STAT_MEDIAN = 17, SCIR_B200_PAD_STAT_MINIMUM = 18, SCIR_B200_PAD_STAT_MAXIMUM = 19 };
 
 /* upfirdn(h, x, up, down), mode='constant' (pyx:421-481): writes outputs m in
@@ -215,6 +230,9 @@ SCIR_B200_API int scir_b200_add_f32(scir_b200_ctx *ctx, const float *d_a, const 
 SCIR_B200_API int scir_b200_mg_create(const int *devices, int n_devices, scir_b200_mg **mg);
 SCIR_B200_API int scir_b200_mg_destroy(scir_b200_mg *mg);
 SCIR_B200_API int scir_b200_mg_device_count(const scir_b200_mg *mg, int *n_devices);
+/* Borrow shard `shard`'s ctx (owned by mg) for scir_b200_malloc / memcpy on that device. */
+SCIR_B200_API int scir_b200_mg_ctx(const scir_b200_mg *mg, int shard, scir_b200_ctx **ctx);
+SCIR_B200_API int scir_b200_mg_sync(scir_b200_mg *mg);                       /* waits for every device's stream */
 /* Row block [row_begin, row_end) of a `batch`-row problem owned by shard `rank` of `world`
  * (contiguous blocks, remainder spread over the first shards).  Pure integer; shared with the
  * one-process-per-GPU launcher so both front ends shard identically. */
@@ -235,10 +253,30 @@ SCIR_B200_API int scir_b200_mg_filtfilt_fir_f32_host(scir_b200_mg *mg,
                                        float *h_y, int64_t ld_y,
                                        int64_t batch, int64_t n);
 
+/* Device-resident shards: d_x[s] / d_y[s] point at shard s's first row ON THE DEVICE OF SHARD s
+ * (scir_b200_shard_rows(batch, world, s) rows, pitch ld_x[s] / ld_y[s]).  Asynchronous on every device's stream;
+ * scir_b200_mg_sync() waits.  Same semantics per row as scir_b200_fir1d_batched_f32. */
+SCIR_B200_API int scir_b200_mg_fir1d_batched_f32(scir_b200_mg *mg,
+                                   const float *const *d_x, const int64_t *ld_x,
+                                   const float *taps, int64_t k, int tap_order,
+                                   float *const *d_y, const int64_t *ld_y,
+                                   int64_t batch, int64_t n);
+/* The optional "whole output on one device" step (north_star (d); SURVEY.md 8(e): never on the hot path): fans the
+ * row shards in to d_dst (batch, n), pitch ld_dst, on the device of shard `dst_shard`.  Peer-to-peer copies over
+ * NVLink, one per shard, each queued on the source device's stream behind that shard's kernel; returns when all
+ * have landed. */
+SCIR_B200_API int scir_b200_mg_gather_rows_f32(scir_b200_mg *mg,
+                                 const float *const *d_shards, const int64_t *ld_shards,
+                                 int dst_shard, float *d_dst, int64_t ld_dst,
+                                 int64_t batch, int64_t n);
+
 /* ---- measurement helpers (bench.py): what the SAME box sustains, as roofline denominators ----- */
 SCIR_B200_API int scir_b200_microbench_ffma(scir_b200_ctx *ctx, int iters, double *tflops);      /* FP32 FFMA peak   */
 SCIR_B200_API int scir_b200_microbench_ffma2(scir_b200_ctx *ctx, int iters, int mix, double *tflops); /* packed FFMA2 (+mix) */
 SCIR_B200_API int scir_b200_microbench_copy(scir_b200_ctx *ctx, size_t bytes, int iters, double *gbps); /* HBM rd+wr */
+/* PCIe ceiling of the *_host entry points: pinned copies of `bytes`, H2D alone, D2H alone, both at once (each way). */
+SCIR_B200_API int scir_b200_microbench_pcie(scir_b200_ctx *ctx, size_t bytes, int iters,
+                              double *h2d_gbs, double *d2h_gbs, double *duplex_each_gbs);
 
 #ifdef __cplusplus
 }

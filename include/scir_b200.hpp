@@ -90,7 +90,11 @@ private:
 inline Context& default_context()
 {
     thread_local std::unique_ptr<Context> c;
-    if (!c) c.reset(new Context(0));       // throws GpuError::BackendUnavailable without a B200: never falls back
+    if (!c) {                              // the thread's CURRENT device; throws GpuError::BackendUnavailable without a B200
+        int dev = 0;
+        check(scir_b200_current_device(&dev));
+        c.reset(new Context(dev));
+    }
     return *c;
 }
 
@@ -111,13 +115,30 @@ inline Array2 fir1d_batched_f32_cuda(const Array2& x, const std::vector<float>& 
     return y;
 }
 
-// lib.rs:515-531 minus the silent fallback (lib.rs:520-523).  Device::Cpu is the reference crate's own
-// CPU loop (lib.rs:1134-1152), which this backend does not carry.
+// The crate's CPU function (lib.rs:1134-1152): f32 multiply then f32 add, newest sample first.  Reached only when
+// the caller names Device::Cpu; nothing on the Device::Cuda arm can end up here.
+inline Array2 fir1d_batched_f32(const Array2& x, const std::vector<float>& taps)
+{
+    Array2 y(x.rows, x.cols);
+    const std::size_t k = taps.size();
+    for (std::size_t b = 0; b < x.rows; ++b)
+        for (std::size_t i = 0; i < x.cols; ++i) {
+            volatile float acc = 0.f;                       // volatile: no contraction of the product into the sum
+            for (std::size_t t = 0; t < k && t <= i; ++t) {
+                volatile float prod = taps[k - 1 - t] * x.data[b * x.cols + i - t];
+                acc = acc + prod;
+            }
+            y.data[b * x.cols + i] = acc;
+        }
+    return y;
+}
+
+// lib.rs:515-531 minus the silent fallback (lib.rs:520-523): Device::Cuda runs on the B200 or throws;
+// Device::Cpu is the crate's own CPU function, as in the reference (lib.rs:517-518).
 inline Array2 fir1d_batched_f32_auto(const Array2& x, const std::vector<float>& taps, Device device)
 {
     if (device == Device::Cuda) return fir1d_batched_f32_cuda(x, taps);
-    throw GpuError(GpuError::Kind::BackendUnavailable,
-                   "Device::Cpu is served by the reference crate's fir1d_batched_f32; scir_b200 is the CUDA backend", SCIR_B200_ERR_NO_DEVICE);
+    return fir1d_batched_f32(x, taps);
 }
 
 // lib.rs:77-190 with real device storage (f32 on the device).
@@ -170,10 +191,12 @@ public:
             release();
         }
     }
-    // Elementwise ops with device dispatch (lib.rs:268-377): the Device::Cuda arms, on the resident pointers.
-    // Bit-identical to the CPU loops lib.rs:206-255, so `_auto` gives the same values on either device.
+    // Elementwise ops with device dispatch (lib.rs:268-377).  Device::Cuda arrays run the kernels on the resident
+    // pointers; Device::Cpu arrays run the crate's own loops (lib.rs:206-255) -- the array's device decides, there
+    // is no fallback from one to the other.  Both give the same bits (one add or mul, no FMA).
     DeviceArray add_scalar_auto(float alpha) const
     {
+        if (device_ == Device::Cpu) return host_map([alpha](float a) { return a + alpha; });
         DeviceArray out = like("add_scalar_auto");
         check(scir_b200_add_scalar_f32(default_context().get(), static_cast<const float*>(dptr_), alpha,
                                        static_cast<float*>(out.dptr_), static_cast<int64_t>(len())));
@@ -181,6 +204,7 @@ public:
     }
     DeviceArray mul_scalar_auto(float alpha) const
     {
+        if (device_ == Device::Cpu) return host_map([alpha](float a) { return a * alpha; });
         DeviceArray out = like("mul_scalar_auto");
         check(scir_b200_mul_scalar_f32(default_context().get(), static_cast<const float*>(dptr_), alpha,
                                        static_cast<float*>(out.dptr_), static_cast<int64_t>(len())));
@@ -189,8 +213,13 @@ public:
     DeviceArray add_auto(const DeviceArray& other) const
     {
         if (shape_ != other.shape_) throw GpuError(GpuError::Kind::ShapeMismatch, "add_auto: shapes differ", SCIR_B200_ERR_SHAPE);   // lib.rs:304-306
-        if (other.device_ != Device::Cuda)
-            throw GpuError(GpuError::Kind::BackendUnavailable, "add_auto: both arrays must be on Device::Cuda", SCIR_B200_ERR_NO_DEVICE);
+        if (other.device_ != device_)
+            throw GpuError(GpuError::Kind::BackendUnavailable, "add_auto: both arrays must be on the same device", SCIR_B200_ERR_NO_DEVICE);
+        if (device_ == Device::Cpu) {
+            DeviceArray out = host_map([](float a) { return a; });
+            for (std::size_t i = 0; i < out.host_.size(); ++i) out.host_[i] = host_[i] + other.host_[i];
+            return out;
+        }
         DeviceArray out = like("add_auto");
         check(scir_b200_add_f32(default_context().get(), static_cast<const float*>(dptr_), static_cast<const float*>(other.dptr_),
                                 static_cast<float*>(out.dptr_), static_cast<int64_t>(len())));
@@ -212,6 +241,14 @@ public:
     }
 
 private:
+    template <typename F>
+    DeviceArray host_map(F f) const                         // Device::Cpu arm: the crate's own loop
+    {
+        DeviceArray out;
+        out.shape_ = shape_; out.dtype_ = dtype_; out.host_.resize(host_.size());
+        for (std::size_t i = 0; i < host_.size(); ++i) out.host_[i] = f(host_[i]);
+        return out;
+    }
     DeviceArray like(const char* what) const               // same shape, fresh device storage
     {
         if (device_ != Device::Cuda)

@@ -51,6 +51,10 @@ SIGNATURES = {
     "scir_b200_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "scir_b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "scir_b200_host_free": (C.c_int, [vp]),
+    "scir_b200_host_register": (C.c_int, [vp, C.c_size_t]),
+    "scir_b200_host_unregister": (C.c_int, [vp]),
+    "scir_b200_host_is_pinned": (C.c_int, [vp, C.c_size_t, C.POINTER(C.c_int)]),
+    "scir_b200_current_device": (C.c_int, [C.POINTER(C.c_int)]),
     "scir_b200_fir1d_batched_f32": (C.c_int, [vp, fp, i64, fp, i64, C.c_int, fp, i64, i64, i64]),
     "scir_b200_fir1d_batched_f32_host": (C.c_int, [vp, fp, i64, fp, i64, C.c_int, fp, i64, i64, i64]),
     "scir_b200_fir1d_batched_f64": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, vp, i64, i64, i64]),
@@ -70,6 +74,10 @@ SIGNATURES = {
     "scir_b200_mg_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
     "scir_b200_mg_destroy": (C.c_int, [vp]),
     "scir_b200_mg_device_count": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "scir_b200_mg_ctx": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "scir_b200_mg_sync": (C.c_int, [vp]),
+    "scir_b200_mg_fir1d_batched_f32": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64), fp, i64, C.c_int, C.POINTER(vp), C.POINTER(i64), i64, i64]),
+    "scir_b200_mg_gather_rows_f32": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64), C.c_int, fp, i64, i64, i64]),
     "scir_b200_shard_rows": (C.c_int, [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]),
     "scir_b200_mg_fir1d_batched_f32_host": (C.c_int, [vp, fp, i64, fp, i64, C.c_int, fp, i64, i64, i64]),
     "scir_b200_mg_resample_poly_f32_host": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64]),
@@ -77,6 +85,7 @@ SIGNATURES = {
     "scir_b200_microbench_ffma": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
     "scir_b200_microbench_ffma2": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "scir_b200_microbench_copy": (C.c_int, [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+    "scir_b200_microbench_pcie": (C.c_int, [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

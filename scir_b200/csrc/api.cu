@@ -2,6 +2,7 @@
 // dispatch that maps scir-signal's FIR routes onto the kernels.  This is the C++ host layer that
 // stands where the reference's `mod cuda` host wrappers stood (crates/scir-gpu/src/lib.rs:840-1113).
 #include "common.cuh"
+#include "copy_pool.hpp"
 
 #include <cmath>
 
@@ -9,6 +10,7 @@
 #include <algorithm>
 #include <new>
 #include <numeric>
+#include <thread>
 
 namespace scir_b200 {
 
@@ -49,6 +51,51 @@ int ctx_bind(const scir_b200_ctx* ctx)
 {
     SCIR_CUDA(cudaSetDevice(ctx->device), "cudaSetDevice");
     return SCIR_B200_OK;
+}
+
+// ---- DeviceScope: the caller's current context survives every ABI call ---------------------------
+namespace {
+typedef int (*CtxGetCurrentFn)(void**);
+typedef int (*CtxSetCurrentFn)(void*);
+struct DriverCtxApi {
+    CtxGetCurrentFn get = nullptr;
+    CtxSetCurrentFn set = nullptr;
+    DriverCtxApi()
+    {
+        void *g = nullptr, *s = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &g, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuCtxSetCurrent", &s, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess) {
+            get = reinterpret_cast<CtxGetCurrentFn>(g);
+            set = reinterpret_cast<CtxSetCurrentFn>(s);
+        } else {
+            cudaGetLastError();
+        }
+    }
+};
+const DriverCtxApi& driver_ctx_api()
+{
+    static const DriverCtxApi api;
+    return api;
+}
+}  // namespace
+
+DeviceScope::DeviceScope(int device)
+{
+    const DriverCtxApi& api = driver_ctx_api();
+    if (api.get && api.get(&prev) == 0) restore = true;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) rc = cuda_error(e, "cudaSetDevice");
+}
+
+DeviceScope::~DeviceScope()
+{
+    if (!restore) return;
+    const DriverCtxApi& api = driver_ctx_api();
+    void* now = nullptr;
+    if (api.get(&now) == 0 && now != prev) api.set(prev);
 }
 
 int ctx_scratch(scir_b200_ctx* ctx, DeviceBuffer& buf, size_t bytes)
@@ -273,42 +320,165 @@ static int resample_device(scir_b200_ctx* ctx, const float* window, int64_t len_
                           pl.n_pre_remove, pl.n_out, ext_mode, cval);
 }
 
-// ---- *_host streaming: rows flow through a 3-slot ring, H2D / kernels / D2H on three streams ---------
+// ---- *_host streaming: rows flow through a ring of row blocks, H2D / kernels / D2H on three streams --------
+// Pinned caller memory (scir_b200_host_alloc / scir_b200_host_register) is DMA'd directly.  Pageable caller memory
+// -- what a Rust Vec / ndarray::Array2 / numpy array is -- would make cudaMemcpyAsync stage through the driver's
+// own bounce buffer on the calling thread, which serialises the three streams; instead the ring gets pinned
+// twins, filled and drained by the ctx's copy threads while the DMA engines and the kernels run (host_stage=1),
+// or the caller's spans are registered for the duration of the call (host_stage=2).
+static bool is_pinned_span(const void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return true;
+    auto pinned = [](const void* q) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    };
+    return pinned(p) && pinned(static_cast<const char*>(p) + bytes - 1);
+}
+
+static int pinned_scratch(scir_b200_ctx* ctx, DeviceBuffer& buf, size_t bytes, unsigned flags)
+{
+    if (buf.bytes >= bytes && buf.ptr != nullptr) return SCIR_B200_OK;
+    if (buf.ptr) {
+        SCIR_CUDA(cudaStreamSynchronize(ctx->s_h2d), "cudaStreamSynchronize");
+        SCIR_CUDA(cudaStreamSynchronize(ctx->s_d2h), "cudaStreamSynchronize");
+        SCIR_CUDA(cudaFreeHost(buf.ptr), "cudaFreeHost(ring)");
+        buf.ptr = nullptr;
+        buf.bytes = 0;
+    }
+    SCIR_CUDA(cudaHostAlloc(&buf.ptr, bytes, flags), "cudaHostAlloc(ring)");
+    buf.bytes = bytes;
+    return SCIR_B200_OK;
+}
+
+struct HostRegistration {          // host_stage=2: registered for the call, released on every exit path
+    void* p = nullptr;
+    int reg(const void* q, size_t bytes)
+    {
+        SCIR_CUDA(cudaHostRegister(const_cast<void*>(q), bytes, cudaHostRegisterPortable), "cudaHostRegister");
+        p = const_cast<void*>(q);
+        return SCIR_B200_OK;
+    }
+    ~HostRegistration()
+    {
+        if (p) cudaHostUnregister(p);
+    }
+};
+
 template <typename Fn>
 static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int64_t n_in, float* h_y,
                          int64_t ld_y, int64_t n_out, int64_t batch, size_t extra_scratch_per_row, Fn&& fn)
 {
+    constexpr int S = scir_b200_ctx::kHostSlots;
     if (batch == 0) return SCIR_B200_OK;
     SCIR_TRY(ctx_bind(ctx));
     if (!ctx->s_h2d) {
         SCIR_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking), "cudaStreamCreate");
         SCIR_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking), "cudaStreamCreate");
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < S; ++i) {
             SCIR_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming), "cudaEventCreate");
             SCIR_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming), "cudaEventCreate");
             SCIR_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming), "cudaEventCreate");
         }
     }
+    const size_t span_x = n_in > 0 ? (static_cast<size_t>(batch - 1) * ld_x + n_in) * 4 : 0;
+    const size_t span_y = n_out > 0 ? (static_cast<size_t>(batch - 1) * ld_y + n_out) * 4 : 0;
+    bool stage_x = n_in > 0 && !is_pinned_span(h_x, span_x);
+    bool stage_y = n_out > 0 && !is_pinned_span(h_y, span_y);
+    HostRegistration reg_x, reg_y;
+    if (ctx->opt.host_stage == 0) stage_x = stage_y = false;
+    if (ctx->opt.host_stage == 2 && (stage_x || stage_y)) {
+        if (stage_x) SCIR_TRY(reg_x.reg(h_x, span_x));
+        if (stage_y) SCIR_TRY(reg_y.reg(h_y, span_y));
+        stage_x = stage_y = false;
+        ctx->host_registered_calls++;
+    }
+    const bool staged = stage_x || stage_y;
+
     const int64_t ldi = (n_in + 3) / 4 * 4, ldo = (n_out + 3) / 4 * 4;
     int64_t rows = ctx->opt.host_block_rows;
     if (rows <= 0) {
+        // 64 MiB of rows per block when DMA-ing caller memory directly; 16 MiB through the pinned ring, so that the
+        // ring (S slots each way) stays small and a block's copy threads finish well inside one block's DMA time
         const size_t per_row = static_cast<size_t>(ldi + ldo) * 4 + extra_scratch_per_row;
-        rows = std::max<int64_t>(1, static_cast<int64_t>((size_t(64) << 20) / std::max<size_t>(per_row, 1)));
+        const size_t target = staged ? (size_t(16) << 20) : (size_t(64) << 20);
+        rows = std::max<int64_t>(1, static_cast<int64_t>(target / std::max<size_t>(per_row, 1)));
     }
     rows = std::min(rows, batch);
-    for (int s = 0; s < 3; ++s) {
-        SCIR_TRY(ctx_scratch(ctx, ctx->stage_in[s], static_cast<size_t>(rows) * std::max<int64_t>(ldi, 4) * 4));
-        SCIR_TRY(ctx_scratch(ctx, ctx->stage_out[s], static_cast<size_t>(rows) * std::max<int64_t>(ldo, 4) * 4));
+    const size_t in_bytes = static_cast<size_t>(rows) * std::max<int64_t>(ldi, 4) * 4;
+    const size_t out_bytes = static_cast<size_t>(rows) * std::max<int64_t>(ldo, 4) * 4;
+    for (int s = 0; s < S; ++s) {
+        SCIR_TRY(ctx_scratch(ctx, ctx->stage_in[s], in_bytes));
+        SCIR_TRY(ctx_scratch(ctx, ctx->stage_out[s], out_bytes));
     }
-    int64_t blk = 0;
-    for (int64_t r0 = 0; r0 < batch; r0 += rows, ++blk) {
-        const int s = static_cast<int>(blk % 3);
-        const int64_t nr = std::min(rows, batch - r0);
+    if (staged) {
+        const bool wc = ctx->opt.host_stage_wc != 0;
+        if (stage_x && ctx->pin_in_wc != wc)
+            for (int s = 0; s < S; ++s)
+                if (ctx->pin_in[s].ptr) {
+                    SCIR_CUDA(cudaStreamSynchronize(ctx->s_h2d), "cudaStreamSynchronize");
+                    SCIR_CUDA(cudaFreeHost(ctx->pin_in[s].ptr), "cudaFreeHost(ring)");
+                    ctx->pin_in[s] = DeviceBuffer{};
+                }
+        ctx->pin_in_wc = wc;
+        for (int s = 0; s < S; ++s) {
+            if (stage_x)
+                SCIR_TRY(pinned_scratch(ctx, ctx->pin_in[s], in_bytes,
+                                        cudaHostAllocPortable | (wc ? cudaHostAllocWriteCombined : 0u)));
+            if (stage_y) SCIR_TRY(pinned_scratch(ctx, ctx->pin_out[s], out_bytes, cudaHostAllocPortable));
+        }
+        int want = static_cast<int>(ctx->opt.host_copy_threads);
+        if (want <= 0) want = std::max(2, std::min(8, static_cast<int>(std::thread::hardware_concurrency()) / 2));
+        if (!ctx->pool || ctx->pool->threads() != want) {
+            delete ctx->pool;
+            ctx->pool = new CopyPool(want);
+        }
+        ctx->host_staged_calls++;
+    }
+
+    // Block b uses slot b % S.  With staging, block b's rows are copied into the pinned slot while block b-1 is on the
+    // bus / in the kernel, and block b-LAG's output is copied out to the caller once its D2H has landed.
+    constexpr int LAG = 3;
+    const int64_t nblk = (batch + rows - 1) / rows;
+    CopyPool::TicketPtr t_out[S], t_in;
+    auto rows_of = [&](int64_t b) { return std::min(rows, batch - b * rows); };
+    auto drain = [&](int64_t b) -> int {                    // pinned slot -> caller's y rows of block b
+        const int s = static_cast<int>(b % S);
+        SCIR_CUDA(cudaEventSynchronize(ctx->ev_out[s]), "cudaEventSynchronize(D2H)");
+        t_out[s] = ctx->pool->submit_2d(reinterpret_cast<char*>(h_y + b * rows * ld_y), static_cast<size_t>(ld_y) * 4,
+                                        static_cast<const char*>(ctx->pin_out[s].ptr), static_cast<size_t>(ldo) * 4,
+                                        static_cast<size_t>(n_out) * 4, static_cast<size_t>(rows_of(b)));
+        return SCIR_B200_OK;
+    };
+    auto run_blocks = [&]() -> int {
+    for (int64_t blk = 0; blk < nblk; ++blk) {
+        const int s = static_cast<int>(blk % S);
+        const int64_t r0 = blk * rows, nr = rows_of(blk);
         float* din = static_cast<float*>(ctx->stage_in[s].ptr);
         float* dout = static_cast<float*>(ctx->stage_out[s].ptr);
-        if (blk >= 3) SCIR_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
+        if (stage_x) {
+            if (blk >= S) SCIR_CUDA(cudaEventSynchronize(ctx->ev_in[s]), "cudaEventSynchronize(H2D)");   // slot's last DMA read done
+            t_in = ctx->pool->submit_2d(static_cast<char*>(ctx->pin_in[s].ptr), static_cast<size_t>(ldi) * 4,
+                                        reinterpret_cast<const char*>(h_x + r0 * ld_x), static_cast<size_t>(ld_x) * 4,
+                                        static_cast<size_t>(n_in) * 4, static_cast<size_t>(nr));
+        }
+        if (stage_y && blk >= LAG) SCIR_TRY(drain(blk - LAG));
+        if (stage_x) ctx->pool->wait(t_in);
+        if (stage_y && t_out[s]) {                          // the slot's previous contents must have reached the caller
+            ctx->pool->wait(t_out[s]);
+            t_out[s].reset();
+        }
+        if (blk >= S) SCIR_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
         if (n_in > 0) {
-            if (ld_x == n_in && ldi == n_in)               // dense rows: one linear DMA
+            if (stage_x)
+                SCIR_CUDA(cudaMemcpyAsync(din, ctx->pin_in[s].ptr, static_cast<size_t>(nr) * ldi * 4, cudaMemcpyHostToDevice,
+                                          ctx->s_h2d),
+                          "cudaMemcpyAsync(H2D)");
+            else if (ld_x == n_in && ldi == n_in)           // dense rows: one linear DMA
                 SCIR_CUDA(cudaMemcpyAsync(din, h_x + r0 * ld_x, static_cast<size_t>(nr) * n_in * 4, cudaMemcpyHostToDevice,
                                           ctx->s_h2d),
                           "cudaMemcpyAsync(H2D)");
@@ -319,12 +489,16 @@ static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int
         }
         SCIR_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->s_h2d), "cudaEventRecord");
         SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0), "cudaStreamWaitEvent");
-        if (blk >= 3) SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0), "cudaStreamWaitEvent");
+        if (blk >= S) SCIR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0), "cudaStreamWaitEvent");
         SCIR_TRY(fn(nr, din, ldi, dout, ldo));
         SCIR_CUDA(cudaEventRecord(ctx->ev_k[s], ctx->stream), "cudaEventRecord");
         SCIR_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[s], 0), "cudaStreamWaitEvent");
         if (n_out > 0) {
-            if (ld_y == n_out && ldo == n_out)
+            if (stage_y)
+                SCIR_CUDA(cudaMemcpyAsync(ctx->pin_out[s].ptr, dout, static_cast<size_t>(nr) * ldo * 4, cudaMemcpyDeviceToHost,
+                                          ctx->s_d2h),
+                          "cudaMemcpyAsync(D2H)");
+            else if (ld_y == n_out && ldo == n_out)
                 SCIR_CUDA(cudaMemcpyAsync(h_y + r0 * ld_y, dout, static_cast<size_t>(nr) * n_out * 4, cudaMemcpyDeviceToHost,
                                           ctx->s_d2h),
                           "cudaMemcpyAsync(D2H)");
@@ -335,9 +509,22 @@ static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int
         }
         SCIR_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->s_d2h), "cudaEventRecord");
     }
-    SCIR_CUDA(cudaStreamSynchronize(ctx->s_d2h), "cudaStreamSynchronize(D2H)");
-    SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
-    SCIR_CUDA(cudaStreamSynchronize(ctx->s_h2d), "cudaStreamSynchronize(H2D)");
+    if (stage_y)
+        for (int64_t b = std::max<int64_t>(0, nblk - LAG); b < nblk; ++b) SCIR_TRY(drain(b));
+    return SCIR_B200_OK;
+    };
+    const int rc = run_blocks();
+    // queued copy jobs reference caller memory: they must have run before this call returns, error or not
+    if (ctx->pool) {
+        ctx->pool->wait(t_in);
+        for (int s = 0; s < S; ++s) ctx->pool->wait(t_out[s]);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_d2h), e2 = cudaStreamSynchronize(ctx->stream),
+                e3 = cudaStreamSynchronize(ctx->s_h2d);
+    if (rc != SCIR_B200_OK) return rc;
+    SCIR_CUDA(e1, "cudaStreamSynchronize(D2H)");
+    SCIR_CUDA(e2, "cudaStreamSynchronize");
+    SCIR_CUDA(e3, "cudaStreamSynchronize(H2D)");
     return SCIR_B200_OK;
 }
 
@@ -380,7 +567,8 @@ static int ctx_make(int device, void* stream, bool borrow, scir_b200_ctx** out)
     if (n == 0) return set_error(SCIR_B200_ERR_NO_DEVICE, "no CUDA device present");
     if (device < 0 || device >= n)
         return set_error(SCIR_B200_ERR_NO_DEVICE, "device %d out of range (have %d)", device, n);
-    SCIR_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    DeviceScope scope(device);
+    SCIR_TRY(scope.rc);
     cudaDeviceProp prop;
     SCIR_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
     if (prop.major != 10)
@@ -416,7 +604,7 @@ int scir_b200_ctx_create_on_stream(int device, void* cuda_stream, scir_b200_ctx*
 int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
 {
     if (!ctx) return SCIR_B200_OK;
-    cudaSetDevice(ctx->device);
+    DeviceScope scope(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
@@ -425,7 +613,10 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
     if (ctx->row_bg.ptr) cudaFree(ctx->row_bg.ptr);
     if (ctx->toep_taps.ptr) cudaFree(ctx->toep_taps.ptr);
     if (ctx->gen_taps.ptr) cudaFree(ctx->gen_taps.ptr);
-    for (int i = 0; i < 3; ++i) {
+    delete ctx->pool;
+    for (int i = 0; i < scir_b200_ctx::kHostSlots; ++i) {
+        if (ctx->pin_in[i].ptr) cudaFreeHost(ctx->pin_in[i].ptr);
+        if (ctx->pin_out[i].ptr) cudaFreeHost(ctx->pin_out[i].ptr);
         if (ctx->stage_in[i].ptr) cudaFree(ctx->stage_in[i].ptr);
         if (ctx->stage_out[i].ptr) cudaFree(ctx->stage_out[i].ptr);
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -441,7 +632,7 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
 
 int scir_b200_ctx_sync(scir_b200_ctx* ctx)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(ctx_bind(ctx));
     SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
     return SCIR_B200_OK;
@@ -482,6 +673,9 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
+    if (!strcmp(key, "host_stage")) return &o.host_stage;
+    if (!strcmp(key, "host_copy_threads")) return &o.host_copy_threads;
+    if (!strcmp(key, "host_stage_wc")) return &o.host_stage_wc;
     return nullptr;
 }
 
@@ -514,6 +708,14 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
         *value = static_cast<int64_t>(ctx->filtfilt_fused_calls);
         return SCIR_B200_OK;
     }
+    if (key && !strcmp(key, "host_staged_calls")) {                   // read-only statistic
+        *value = static_cast<int64_t>(ctx->host_staged_calls);
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "host_registered_calls")) {               // read-only statistic
+        *value = static_cast<int64_t>(ctx->host_registered_calls);
+        return SCIR_B200_OK;
+    }
     if (key && !strcmp(key, "poly_launches")) {                       // read-only statistic
         *value = static_cast<int64_t>(ctx->poly_launches);
         return SCIR_B200_OK;
@@ -535,7 +737,7 @@ int scir_b200_ctx_launch_count(const scir_b200_ctx* ctx, uint64_t* count)
 // ---- memory ------------------------------------------------------------------------------------------
 int scir_b200_malloc(scir_b200_ctx* ctx, size_t bytes, void** d_ptr)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!d_ptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "d_ptr is NULL");
     *d_ptr = nullptr;
     if (bytes == 0) return SCIR_B200_OK;
@@ -546,7 +748,7 @@ int scir_b200_malloc(scir_b200_ctx* ctx, size_t bytes, void** d_ptr)
 
 int scir_b200_free(scir_b200_ctx* ctx, void* d_ptr)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!d_ptr) return SCIR_B200_OK;
     SCIR_TRY(ctx_bind(ctx));
     SCIR_CUDA(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
@@ -556,7 +758,7 @@ int scir_b200_free(scir_b200_ctx* ctx, void* d_ptr)
 
 int scir_b200_memcpy_h2d(scir_b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (bytes == 0) return SCIR_B200_OK;
     if (!d_dst || !h_src) return set_error(SCIR_B200_ERR_INVALID_ARG, "memcpy_h2d: NULL pointer");
     SCIR_TRY(ctx_bind(ctx));
@@ -567,7 +769,7 @@ int scir_b200_memcpy_h2d(scir_b200_ctx* ctx, void* d_dst, const void* h_src, siz
 
 int scir_b200_memcpy_d2h(scir_b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (bytes == 0) return SCIR_B200_OK;
     if (!h_dst || !d_src) return set_error(SCIR_B200_ERR_INVALID_ARG, "memcpy_d2h: NULL pointer");
     SCIR_TRY(ctx_bind(ctx));
@@ -592,11 +794,54 @@ int scir_b200_host_free(void* h_ptr)
     return SCIR_B200_OK;
 }
 
+int scir_b200_host_register(void* h_ptr, size_t bytes)
+{
+    if (!h_ptr || bytes == 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "host_register: NULL pointer or zero size");
+    cudaError_t e = cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return SCIR_B200_OK;
+    }
+    SCIR_CUDA(e, "cudaHostRegister");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_host_unregister(void* h_ptr)
+{
+    if (!h_ptr) return SCIR_B200_OK;
+    SCIR_CUDA(cudaHostUnregister(h_ptr), "cudaHostUnregister");
+    return SCIR_B200_OK;
+}
+
+int scir_b200_host_is_pinned(const void* h_ptr, size_t bytes, int* pinned)
+{
+    if (!pinned) return set_error(SCIR_B200_ERR_INVALID_ARG, "pinned is NULL");
+    *pinned = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount");
+    if (n == 0) return set_error(SCIR_B200_ERR_NO_DEVICE, "no CUDA device present");
+    *pinned = (h_ptr != nullptr && bytes > 0 && is_pinned_span(h_ptr, bytes)) ? 1 : 0;
+    return SCIR_B200_OK;
+}
+
+int scir_b200_current_device(int* device)
+{
+    if (!device) return set_error(SCIR_B200_ERR_INVALID_ARG, "device is NULL");
+    *device = -1;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount");
+    if (n == 0) return set_error(SCIR_B200_ERR_NO_DEVICE, "no CUDA device present");
+    SCIR_CUDA(cudaGetDevice(device), "cudaGetDevice");
+    return SCIR_B200_OK;
+}
+
 // ---- hot path ------------------------------------------------------------------------------------------
 int scir_b200_fir1d_batched_f32(scir_b200_ctx* ctx, const float* d_x, int64_t ld_x, const float* taps, int64_t k,
                                 int tap_order, float* d_y, int64_t ld_y, int64_t batch, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_taps(taps, k));
     if (tap_order != SCIR_B200_TAPS_SCIR && tap_order != SCIR_B200_TAPS_LFILTER)
         return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
@@ -611,7 +856,7 @@ int scir_b200_fir1d_batched_f32(scir_b200_ctx* ctx, const float* d_x, int64_t ld
 int scir_b200_fir1d_batched_f32_host(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, const float* taps,
                                      int64_t k, int tap_order, float* h_y, int64_t ld_y, int64_t batch, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_taps(taps, k));
     if (tap_order != SCIR_B200_TAPS_SCIR && tap_order != SCIR_B200_TAPS_LFILTER)
         return set_error(SCIR_B200_ERR_INVALID_ARG, "unknown tap_order %d", tap_order);
@@ -630,7 +875,7 @@ int scir_b200_lfilter_fir_f32(scir_b200_ctx* ctx, const float* b, int64_t k, flo
                               int64_t ld_x, const float* d_zi, float* d_zf, float* d_y, int64_t ld_y,
                               int64_t batch, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_taps(b, k));
     if (a0 == 0.f) return set_error(SCIR_B200_ERR_INVALID_ARG, "a[0] must be nonzero");
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
@@ -653,7 +898,7 @@ int scir_b200_upfirdn_f32(scir_b200_ctx* ctx, const float* h, int64_t len_h, int
                           const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y, int64_t ld_y,
                           int64_t m_begin, int64_t m_count)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!h || len_h < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "h must hold at least one tap");
     if (up < 1 || down < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "up and down must be >= 1");   // _upfirdn.py:98
     if (n_in < 1 && batch > 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "upfirdn needs n_in >= 1");
@@ -680,7 +925,7 @@ int scir_b200_resample_poly_f32(scir_b200_ctx* ctx, const float* window, int64_t
                                 const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
                                 int64_t ld_y)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     scir_b200_resample_plan pl;
     if (!window) return set_error(SCIR_B200_ERR_INVALID_ARG, "window is NULL");
     SCIR_TRY(scir_b200_resample_poly_plan(n_in, len_h, up, down, &pl));
@@ -695,7 +940,7 @@ int scir_b200_upfirdn_mode_f32(scir_b200_ctx* ctx, const float* h, int64_t len_h
                                float cval, const float* d_x, int64_t ld_x, int64_t batch, int64_t n_in, float* d_y,
                                int64_t ld_y, int64_t m_begin, int64_t m_count)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!h || len_h < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "h must hold at least one tap");
     if (up < 1 || down < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "up and down must be >= 1");   // _upfirdn.py:98
     if (n_in < 1 && batch > 0) return set_error(SCIR_B200_ERR_INVALID_ARG, "upfirdn needs n_in >= 1");
@@ -713,7 +958,7 @@ int scir_b200_resample_poly_pad_f32(scir_b200_ctx* ctx, const float* window, int
                                     int padtype, float cval, const float* d_x, int64_t ld_x, int64_t batch,
                                     int64_t n_in, float* d_y, int64_t ld_y)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     scir_b200_resample_plan pl;
     if (!window) return set_error(SCIR_B200_ERR_INVALID_ARG, "window is NULL");
     SCIR_TRY(scir_b200_resample_poly_plan(n_in, len_h, up, down, &pl));
@@ -754,7 +999,7 @@ int scir_b200_resample_poly_f32_host(scir_b200_ctx* ctx, const float* window, in
                                      int64_t down, const float* h_x, int64_t ld_x, int64_t batch, int64_t n_in,
                                      float* h_y, int64_t ld_y)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     scir_b200_resample_plan pl;
     if (!window) return set_error(SCIR_B200_ERR_INVALID_ARG, "window is NULL");
     SCIR_TRY(scir_b200_resample_poly_plan(n_in, len_h, up, down, &pl));
@@ -770,7 +1015,7 @@ int scir_b200_resample_poly_f32_host(scir_b200_ctx* ctx, const float* window, in
 int scir_b200_filtfilt_fir_f32(scir_b200_ctx* ctx, const float* b, int64_t k, int pad_mode, int64_t padlen,
                                const float* d_x, int64_t ld_x, float* d_y, int64_t ld_y, int64_t batch, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_taps(b, k));
     SCIR_TRY(check_matrix(d_x, ld_x, batch, n, "x"));
     SCIR_TRY(check_matrix(d_y, ld_y, batch, n, "y"));
@@ -782,7 +1027,7 @@ int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx* ctx, const float* b, int64_t 
                                     const float* h_x, int64_t ld_x, float* h_y, int64_t ld_y, int64_t batch,
                                     int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_taps(b, k));
     SCIR_TRY(check_matrix(h_x, ld_x, batch, n, "x"));
     SCIR_TRY(check_matrix(h_y, ld_y, batch, n, "y"));
@@ -796,7 +1041,7 @@ int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx* ctx, const float* b, int64_t 
 int scir_b200_fir1d_batched_f64(scir_b200_ctx* ctx, const double* d_x, int64_t ld_x, const double* taps, int64_t k,
                                 int tap_order, double* d_y, int64_t ld_y, int64_t batch, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (taps == nullptr) return set_error(SCIR_B200_ERR_INVALID_ARG, "taps is NULL");
     if (k < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "need at least one tap (k=%lld)", (long long)k);
     if (tap_order != SCIR_B200_TAPS_SCIR && tap_order != SCIR_B200_TAPS_LFILTER)
@@ -819,7 +1064,7 @@ static int check_vec(const void* p, int64_t n, const char* name)
 
 int scir_b200_add_scalar_f32(scir_b200_ctx* ctx, const float* d_a, float alpha, float* d_y, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_vec(d_a, n, "a"));
     SCIR_TRY(check_vec(d_y, n, "y"));
     return launch_elementwise(ctx, 0, d_a, nullptr, alpha, d_y, n);
@@ -827,7 +1072,7 @@ int scir_b200_add_scalar_f32(scir_b200_ctx* ctx, const float* d_a, float alpha, 
 
 int scir_b200_mul_scalar_f32(scir_b200_ctx* ctx, const float* d_a, float alpha, float* d_y, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_vec(d_a, n, "a"));
     SCIR_TRY(check_vec(d_y, n, "y"));
     return launch_elementwise(ctx, 1, d_a, nullptr, alpha, d_y, n);
@@ -835,7 +1080,7 @@ int scir_b200_mul_scalar_f32(scir_b200_ctx* ctx, const float* d_a, float alpha, 
 
 int scir_b200_add_f32(scir_b200_ctx* ctx, const float* d_a, const float* d_b, float* d_y, int64_t n)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     SCIR_TRY(check_vec(d_a, n, "a"));
     SCIR_TRY(check_vec(d_b, n, "b"));
     SCIR_TRY(check_vec(d_y, n, "y"));

@@ -30,6 +30,28 @@ void clear_error();
         if (_rc != SCIR_B200_OK) return _rc; \
     } while (0)
 
+// Every ABI entry point that takes a ctx opens with SCIR_ENTER(ctx): NULL check, then the ctx's device is made
+// current for the duration of the call and the CALLER's current context is put back on return (DeviceScope), so a
+// call on a cuda:1 ctx inside a PyTorch process never moves torch's current device.
+#define SCIR_ENTER(ctx)                                    \
+    SCIR_TRY(::scir_b200::check_ctx(ctx));                 \
+    ::scir_b200::DeviceScope _scir_scope((ctx)->device);   \
+    SCIR_TRY(_scir_scope.rc)
+
+// Saves the calling thread's current CUDA context, binds `device`, restores on destruction.  The driver's
+// cuCtxGetCurrent / cuCtxSetCurrent (resolved through cudaGetDriverEntryPoint: no link-time libcuda dependency)
+// are used rather than cudaGetDevice / cudaSetDevice, because restoring "device 0" with cudaSetDevice in a thread
+// that never touched the GPU would CREATE a primary context on device 0 (CUDA >= 12 initialises eagerly).
+struct DeviceScope {
+    void* prev = nullptr;      // CUcontext
+    bool restore = false;
+    int rc = SCIR_B200_OK;
+    explicit DeviceScope(int device);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 // ---- context ----------------------------------------------------------------------------------
 struct Options {
     int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
@@ -48,7 +70,15 @@ struct Options {
     int64_t toeplitz_min_k = 1024; // auto mode: tap counts from here on always take the tensor path
     int64_t toeplitz_min_k_full = 2;  // auto mode: ... and from here on when the cost model (api.cu: prefer_toeplitz) says so
     int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
+    // *_host entry points, when the caller's arrays are PAGEABLE (a Rust Vec / ndarray / numpy buffer):
+    int64_t host_stage = 1;      // 1 stage through the ctx's pinned ring with copy threads (default); 0 hand the pageable
+                                 // pointer to cudaMemcpyAsync (driver-staged, host-synchronous: the A/B arm);
+                                 // 2 cudaHostRegister the caller's spans for the duration of the call
+    int64_t host_copy_threads = 0;   // copy threads of the pinned ring (0 = auto: min(8, hardware threads / 2))
+    int64_t host_stage_wc = 0;   // 1: the H2D half of the pinned ring is write-combined memory
 };
+
+class CopyPool;                 // copy_pool.hpp
 
 struct DeviceBuffer {           // RAII-free growable scratch owned by the ctx
     void* ptr = nullptr;
@@ -77,12 +107,19 @@ struct scir_b200_ctx {
     std::vector<float> gen_taps_host;      // ... and what the buffer currently holds
     uint64_t gen_tiled_launches = 0;       // launches served by it
     scir_b200::DeviceBuffer row_bg;        // resample_poly padtype statistics: one float per row
-    // *_host streaming pipeline resources (lazily created)
+    // *_host streaming pipeline resources (lazily created): a ring of kHostSlots row blocks
+    static constexpr int kHostSlots = 6;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    scir_b200::DeviceBuffer stage_in[3], stage_out[3];
-    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_out[3] = {nullptr, nullptr, nullptr};
+    scir_b200::DeviceBuffer stage_in[kHostSlots], stage_out[kHostSlots];
+    cudaEvent_t ev_in[kHostSlots] = {};
+    cudaEvent_t ev_k[kHostSlots] = {};
+    cudaEvent_t ev_out[kHostSlots] = {};
+    // pageable callers: pinned twins of the ring and the threads that fill / drain them
+    scir_b200::DeviceBuffer pin_in[kHostSlots], pin_out[kHostSlots];
+    bool pin_in_wc = false;
+    scir_b200::CopyPool* pool = nullptr;
+    uint64_t host_staged_calls = 0;        // *_host calls that went through the pinned ring
+    uint64_t host_registered_calls = 0;    // ... that registered the caller's spans instead
 };
 
 namespace scir_b200 {

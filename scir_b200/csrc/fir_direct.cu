@@ -34,6 +34,8 @@
 // extension are properties of the tile LOADER (edge tiles only); interior tiles always take the
 // bulk-copy path.  See DESIGN.md section 4.
 #include "common.cuh"
+
+#include <memory>
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -467,8 +469,8 @@ template <int KC, int DIR, int MAXK>
 int launch_tile(scir_b200_ctx* ctx, const FirTileParams& q, const float* c, int64_t k, long long total)
 {
     // zero-padded host staging; the launch copies it into the parameter buffer synchronously
-    thread_local TapsParam<MAXK>* tl = nullptr;
-    if (!tl) tl = new TapsParam<MAXK>();
+    thread_local std::unique_ptr<TapsParam<MAXK>> tl;       // freed when the thread exits
+    if (!tl) tl.reset(new TapsParam<MAXK>());
     for (int i = 0; i < MAXK; ++i) tl->c[i] = (i < k) ? c[i] : 0.f;
     if (MAXK <= kPackedMaxK)
         for (int i = 0; i < MAXK; ++i) tl->c1[i] = (i + 1 < k) ? c[i + 1] : 0.f;

@@ -3,6 +3,9 @@
 // the FIR kernel uses (FFMA R, R.reuse, UR, R), and a plain float4 copy for HBM read+write.
 #include "common.cuh"
 
+#include <string.h>
+#include <algorithm>
+
 namespace scir_b200 {
 
 struct MbTaps {
@@ -86,7 +89,7 @@ extern "C" {
 
 int scir_b200_microbench_ffma(scir_b200_ctx* ctx, int iters, double* tflops)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!tflops || iters < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
     SCIR_TRY(ctx_bind(ctx));
     constexpr int R = 20;
@@ -117,7 +120,7 @@ int scir_b200_microbench_ffma(scir_b200_ctx* ctx, int iters, double* tflops)
 // mix = 0: pure FFMA2 stream; mix = 1, 2, 4, 8: that many extra integer instructions per 8 FFMA2
 int scir_b200_microbench_ffma2(scir_b200_ctx* ctx, int iters, int mix, double* tflops)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!tflops || iters < 1) return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
     SCIR_TRY(ctx_bind(ctx));
     constexpr int R2 = 10;
@@ -156,7 +159,7 @@ int scir_b200_microbench_ffma2(scir_b200_ctx* ctx, int iters, int mix, double* t
 
 int scir_b200_microbench_copy(scir_b200_ctx* ctx, size_t bytes, int iters, double* gbps)
 {
-    SCIR_TRY(check_ctx(ctx));
+    SCIR_ENTER(ctx);
     if (!gbps || iters < 1 || bytes < 16) return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
     SCIR_TRY(ctx_bind(ctx));
     const size_t n4 = bytes / 16;
@@ -187,6 +190,80 @@ int scir_b200_microbench_copy(scir_b200_ctx* ctx, size_t bytes, int iters, doubl
     cudaFree(a);
     cudaFree(b);
     return SCIR_B200_OK;
+}
+
+// What the PCIe link of THIS box moves with plain pinned copies, as the ceiling for the *_host entry points: `bytes`
+// each way, H2D alone, D2H alone, and both at once on two streams (the *_host ring's steady state).  Best of `iters`.
+int scir_b200_microbench_pcie(scir_b200_ctx* ctx, size_t bytes, int iters, double* h2d_gbs, double* d2h_gbs,
+                              double* duplex_each_gbs)
+{
+    SCIR_ENTER(ctx);
+    if (!h2d_gbs || !d2h_gbs || !duplex_each_gbs || iters < 1 || bytes < 4096)
+        return set_error(SCIR_B200_ERR_INVALID_ARG, "bad microbench arguments");
+    void *ha = nullptr, *hb = nullptr, *da = nullptr, *db = nullptr;
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    auto cleanup = [&]() {
+        if (ha) cudaFreeHost(ha);
+        if (hb) cudaFreeHost(hb);
+        if (da) cudaFree(da);
+        if (db) cudaFree(db);
+        if (s1) cudaStreamDestroy(s1);
+        if (s2) cudaStreamDestroy(s2);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (e2) cudaEventDestroy(e2);
+    };
+    auto body = [&]() -> int {
+        SCIR_CUDA(cudaHostAlloc(&ha, bytes, cudaHostAllocPortable), "cudaHostAlloc");
+        SCIR_CUDA(cudaHostAlloc(&hb, bytes, cudaHostAllocPortable), "cudaHostAlloc");
+        memset(ha, 1, bytes);
+        memset(hb, 2, bytes);
+        SCIR_CUDA(cudaMalloc(&da, bytes), "cudaMalloc");
+        SCIR_CUDA(cudaMalloc(&db, bytes), "cudaMalloc");
+        SCIR_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking), "cudaStreamCreate");
+        SCIR_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking), "cudaStreamCreate");
+        SCIR_CUDA(cudaEventCreate(&e0), "cudaEventCreate");
+        SCIR_CUDA(cudaEventCreate(&e1), "cudaEventCreate");
+        SCIR_CUDA(cudaEventCreate(&e2), "cudaEventCreate");
+        SCIR_CUDA(cudaMemcpyAsync(da, ha, bytes, cudaMemcpyHostToDevice, s1), "warm-up H2D");
+        SCIR_CUDA(cudaMemcpyAsync(hb, db, bytes, cudaMemcpyDeviceToHost, s2), "warm-up D2H");
+        SCIR_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+        double best_h = 0.0, best_d = 0.0, best_x = 0.0;
+        for (int it = 0; it < iters; ++it) {
+            float ms = 0.f;
+            SCIR_CUDA(cudaEventRecord(e0, s1), "cudaEventRecord");
+            SCIR_CUDA(cudaMemcpyAsync(da, ha, bytes, cudaMemcpyHostToDevice, s1), "H2D");
+            SCIR_CUDA(cudaEventRecord(e1, s1), "cudaEventRecord");
+            SCIR_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+            SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+            best_h = std::max(best_h, bytes / (ms * 1e-3) / 1e9);
+            SCIR_CUDA(cudaEventRecord(e0, s2), "cudaEventRecord");
+            SCIR_CUDA(cudaMemcpyAsync(hb, db, bytes, cudaMemcpyDeviceToHost, s2), "D2H");
+            SCIR_CUDA(cudaEventRecord(e1, s2), "cudaEventRecord");
+            SCIR_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+            SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+            best_d = std::max(best_d, bytes / (ms * 1e-3) / 1e9);
+            // both directions at once: s2 starts when s1 starts; the slower stream's end closes the interval
+            SCIR_CUDA(cudaEventRecord(e0, s1), "cudaEventRecord");
+            SCIR_CUDA(cudaStreamWaitEvent(s2, e0, 0), "cudaStreamWaitEvent");
+            SCIR_CUDA(cudaMemcpyAsync(da, ha, bytes, cudaMemcpyHostToDevice, s1), "H2D");
+            SCIR_CUDA(cudaMemcpyAsync(hb, db, bytes, cudaMemcpyDeviceToHost, s2), "D2H");
+            SCIR_CUDA(cudaEventRecord(e2, s2), "cudaEventRecord");
+            SCIR_CUDA(cudaStreamWaitEvent(s1, e2, 0), "cudaStreamWaitEvent");
+            SCIR_CUDA(cudaEventRecord(e1, s1), "cudaEventRecord");
+            SCIR_CUDA(cudaEventSynchronize(e1), "cudaEventSynchronize");
+            SCIR_CUDA(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime");
+            best_x = std::max(best_x, bytes / (ms * 1e-3) / 1e9);
+        }
+        *h2d_gbs = best_h;
+        *d2h_gbs = best_d;
+        *duplex_each_gbs = best_x;
+        return SCIR_B200_OK;
+    };
+    const int rc = body();
+    cleanup();
+    return rc;
 }
 
 }  // extern "C"

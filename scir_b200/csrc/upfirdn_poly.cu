@@ -21,6 +21,8 @@
 //     (config 4: 96 taps -> exactly 32 FFMA per output).
 //   * outputs go back through shared memory and one bulk store.
 #include "common.cuh"
+
+#include <memory>
 #include "ptx.cuh"
 #include "upfirdn_ext.cuh"
 
@@ -509,8 +511,9 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
     const size_t len = static_cast<size_t>(halo) + kPolyNT * SIN + 4;
     const size_t stream_bytes = (2 * len + static_cast<size_t>(kPolyNT) * R) * sizeof(float);
     const int d = ctx->device & 15;
-    thread_local PolyPairs* pairs = nullptr;
-    if (!pairs) pairs = new PolyPairs();
+    thread_local std::unique_ptr<PolyPairs> pairs_owner;    // freed when the thread exits
+    if (!pairs_owner) pairs_owner.reset(new PolyPairs());
+    PolyPairs* pairs = pairs_owner.get();
     // upfirdn_variant: 0 auto (streaming, FFMA2) | 3 one tile per CTA (FFMA2) | 4 streaming, scalar FFMA | 5 tile, scalar FFMA
     const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4 && ctx->opt.upfirdn_variant != 5) ? 1 : 0;   // 6: warp-pipelined (FFMA2)
     if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
@@ -643,8 +646,8 @@ int launch_upfirdn_poly(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64
     const int64_t nchunk = (kp + KCP - 1) / KCP;
     if ((nchunk * KCP + 2) * up > kPolyMaxH) return SCIR_B200_OK;     // filter too long for the parameter block
 
-    thread_local PolyTaps* tl = nullptr;
-    if (!tl) tl = new PolyTaps();
+    thread_local std::unique_ptr<PolyTaps> tl;              // freed when the thread exits
+    if (!tl) tl.reset(new PolyTaps());
     for (int i = 0; i < kPolyMaxH; ++i) tl->c[i] = (i < hi) ? h[i] : 0.f;
 
     PolyParams q{};

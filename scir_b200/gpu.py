@@ -11,8 +11,9 @@ Differences, all required by BASELINE.json's north_star:
   * no silent CPU fallback (lib.rs:520-523): Device.Cuda raises GpuError if the CUDA library or a
     B200 is missing; `fir1d_batched_f32_auto` is infallible in Rust, so the binding panics there --
     here it raises.
-  * Device.Cpu is not served by this backend (the CPU baseline stays the reference crate's own
-    `fir1d_batched_f32`, lib.rs:1134-1152); asking for it raises BackendUnavailable.
+  * Device.Cpu, when asked for EXPLICITLY, runs the crate's own CPU function `fir1d_batched_f32`
+    (lib.rs:1134-1152, restated below) exactly as `_auto` does in the reference (lib.rs:517-518).  It is
+    never a fallback: nothing on the Device.Cuda arm can reach it.
   * DeviceArray is genuinely device-backed after `to_device(Device.Cuda)` (lib.rs:177 is a placeholder).
 
 Arrays: numpy (host; goes through the *_host ABI calls: H2D + kernel + D2H) or torch CUDA tensors
@@ -122,8 +123,19 @@ _ctx_lock = threading.Lock()
 _ctx_cache: dict = {}
 
 
-def default_context(device: int = 0) -> Context:
-    """One library-owned-stream ctx per (thread, device)."""
+def current_device() -> int:
+    """The calling thread's current CUDA device (cudaGetDevice): what torch.cuda.set_device / torchrun's LOCAL_RANK
+    binding selected.  Raises GpuError when there is no GPU."""
+    d = C.c_int(-1)
+    _check(_load().scir_b200_current_device(C.byref(d)))
+    return d.value
+
+
+def default_context(device: int | None = None) -> Context:
+    """One library-owned-stream ctx per (thread, device).  `device=None` means the thread's CURRENT device, so host
+    arrays in a multi-GPU process (one rank per GPU) are filtered on the rank's own GPU, not on GPU 0."""
+    if device is None:
+        device = current_device()
     key = ("own", threading.get_ident(), device)
     with _ctx_lock:
         if key not in _ctx_cache:
@@ -168,6 +180,34 @@ def _host_matrix(x) -> np.ndarray:
     return a
 
 
+def _check_out_host(out, shape) -> int:
+    """Validates a caller-provided host result array and returns its row pitch in elements."""
+    if not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.ndim != 2 or tuple(out.shape) != tuple(shape):
+        raise GpuError.shape_mismatch(f"out must be a float32 numpy array of shape {tuple(shape)}")
+    if not out.flags.writeable:
+        raise GpuError.shape_mismatch("out is read-only")
+    b, n = shape
+    if n > 1 and out.strides[1] != 4:
+        raise GpuError.shape_mismatch("out rows must be contiguous (stride 1 along the samples)")
+    if b > 1 and (out.strides[0] % 4 != 0 or out.strides[0] < 4 * n):
+        raise GpuError.shape_mismatch("out row pitch must be a non-negative multiple of 4 bytes >= the row length")
+    return out.strides[0] // 4 if b > 1 else max(n, 1)
+
+
+def _check_out_torch(out, x) -> int:
+    import torch
+    if not _is_torch(out) or out.dtype != torch.float32 or out.dim() != 2 or tuple(out.shape) != tuple(x.shape):
+        raise GpuError.shape_mismatch(f"out must be a float32 tensor of shape {tuple(x.shape)}")
+    if not out.is_cuda or out.device != x.device:
+        raise GpuError.shape_mismatch(f"out must live on {x.device}, not {out.device}")
+    b, n = x.shape
+    if n > 1 and out.stride(1) != 1:
+        raise GpuError.shape_mismatch("out rows must be contiguous (stride 1 along the samples)")
+    if b > 1 and out.stride(0) < n:
+        raise GpuError.shape_mismatch("out row pitch is shorter than a row")
+    return out.stride(0) if b > 1 else max(n, 1)
+
+
 def _torch_matrix(x):
     import torch
     if x.dtype != torch.float32 or x.dim() != 2 or not x.is_cuda:
@@ -188,17 +228,24 @@ def fir1d_batched_f32_cuda(x, taps, *, ctx: Context | None = None, out=None,
         import torch
         xt, ldx = _torch_matrix(x)
         c = ctx or torch_context(xt)
-        y = torch.empty_like(xt, memory_format=torch.contiguous_format) if out is None else out
         b, n = xt.shape
+        if out is None:
+            y = torch.empty_like(xt, memory_format=torch.contiguous_format)
+            ldy = max(n, 1)
+        else:
+            y, ldy = out, _check_out_torch(out, xt)
         _check(lib.scir_b200_fir1d_batched_f32(c.handle, xt.data_ptr(), ldx, _ptr(t), t.size, tap_order,
-                                               y.data_ptr(), y.stride(0) if b > 1 else max(n, 1), b, n))
+                                               y.data_ptr(), ldy, b, n))
         return y
     a = _host_matrix(x)
-    c = ctx or default_context(0)
+    c = ctx or default_context()
     b, n = a.shape
-    y = np.empty_like(a) if out is None else out
+    if out is None:
+        y, ldy = np.empty_like(a), max(n, 1)
+    else:
+        y, ldy = out, _check_out_host(out, a.shape)
     _check(lib.scir_b200_fir1d_batched_f32_host(c.handle, _ptr(a), max(n, 1), _ptr(t), t.size, tap_order,
-                                                _ptr(y), max(n, 1), b, n))
+                                                _ptr(y), ldy, b, n))
     return y
 
 
@@ -223,7 +270,7 @@ def fir1d_batched_f64_cuda(x, taps, *, ctx: Context | None = None, tap_order: in
     a = np.ascontiguousarray(x, dtype=np.float64)
     if a.ndim != 2:
         raise GpuError.shape_mismatch("x must be 2-D (batch, n)")
-    c = ctx or default_context(0)
+    c = ctx or default_context()
     b, n = a.shape
     y = np.empty_like(a)
     px, py = C.c_void_p(), C.c_void_p()
@@ -239,13 +286,33 @@ def fir1d_batched_f64_cuda(x, taps, *, ctx: Context | None = None, tap_order: in
     return y
 
 
+def fir1d_batched_f32(x, taps) -> np.ndarray:
+    """The crate's CPU function (lib.rs:1134-1152), kept because `fir1d_batched_f32_auto(.., Device::Cpu)` and the
+    crate's public surface name it: y[b,i] = sum_{t=0}^{min(i,k-1)} taps[k-1-t] * x[b,i-t], f32 multiply then f32
+    add, newest sample first.  It is reached ONLY when the caller asks for Device.Cpu explicitly -- never from the
+    Device.Cuda arm, which raises when the GPU path cannot run.  Vectorised over the samples with the reference's
+    per-element operation order, so the values are bit-identical to its loop."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    t = np.ascontiguousarray(taps, dtype=np.float32)
+    if a.ndim != 2 or t.ndim != 1:
+        raise GpuError.shape_mismatch("x must be 2-D (batch, n) and taps 1-D")
+    n, k = a.shape[1], t.size
+    y = np.zeros_like(a)
+    for d in range(min(k, n)):                              # d = t in lib.rs:1141: newest sample first
+        y[:, d:] += t[k - 1 - d] * a[:, : n - d]            # f32 product rounded, then f32 sum rounded (no FMA)
+    return y
+
+
 def fir1d_batched_f32_auto(x, taps, device: Device, **kw):
-    """lib.rs:515-531, minus the silent fallback."""
+    """lib.rs:515-531, minus the silent fallback: Device.Cuda runs on the B200 or raises; Device.Cpu is the crate's
+    own CPU function, as in the reference (lib.rs:517-518)."""
     if device == Device.Cuda:
         return fir1d_batched_f32_cuda(x, taps, **kw)
-    raise GpuError.backend_unavailable(
-        "Device.Cpu is served by the reference crate's own fir1d_batched_f32 (lib.rs:1134-1152); "
-        "scir_b200 is the CUDA backend and has no CPU path")
+    if device == Device.Cpu:
+        if _is_torch(x):
+            raise GpuError.shape_mismatch("Device.Cpu takes host arrays")
+        return fir1d_batched_f32(x, taps)
+    raise GpuError.backend_unavailable(f"unknown device {device!r}")
 
 
 class DeviceArray:
@@ -286,7 +353,7 @@ class DeviceArray:
         if device == Device.Cuda:
             if self._dtype != DType.F32:
                 raise GpuError.backend_unavailable("only f32 arrays live on the device")
-            self._ctx = ctx or default_context(0)
+            self._ctx = ctx or default_context()
             p = C.c_void_p()
             _check(lib.scir_b200_malloc(self._ctx.handle, max(self._host.nbytes, 4), C.byref(p)))
             _check(lib.scir_b200_memcpy_h2d(self._ctx.handle, p, _ptr(self._host), self._host.nbytes))
@@ -311,18 +378,25 @@ class DeviceArray:
     def _need_cuda(self, what):
         if self._device != Device.Cuda:
             raise GpuError.backend_unavailable(
-                f"{what}: Device.Cpu arrays are served by the reference crate's own CPU loops (lib.rs:206-255); "
-                "scir_b200 is the CUDA backend and has no CPU path")
+                f"{what}: operands live on different devices; move them with to_device() first")
+
+    def _host_result(self, values) -> "DeviceArray":
+        return DeviceArray(self._shape, self._dtype, np.asarray(values, dtype=self._host.dtype))
 
     def add_scalar_auto(self, alpha: float) -> "DeviceArray":
-        """lib.rs:268-301, Device::Cuda arm (add_scalar_f32_cuda :912-972) on device-resident data."""
+        """lib.rs:268-301: Device::Cuda arm (add_scalar_f32_cuda :912-972) on device-resident data; a Device.Cpu
+        array runs the crate's own loop (:206-221).  The array's device decides; neither arm falls back to the other."""
+        if self._device == Device.Cpu:
+            return self._host_result(self._host + self._host.dtype.type(alpha))
         self._need_cuda("add_scalar_auto")
         out = self._new_like()
         _check(_load().scir_b200_add_scalar_f32(self._ctx.handle, self._dptr, float(alpha), out._dptr, self._host.size))
         return out
 
     def mul_scalar_auto(self, alpha: float) -> "DeviceArray":
-        """lib.rs:355-388, Device::Cuda arm (mul_scalar_f32_cuda :974-1034)."""
+        """lib.rs:355-388, Device::Cuda arm (mul_scalar_f32_cuda :974-1034); Device.Cpu: the loop :240-255."""
+        if self._device == Device.Cpu:
+            return self._host_result(self._host * self._host.dtype.type(alpha))
         self._need_cuda("mul_scalar_auto")
         out = self._new_like()
         _check(_load().scir_b200_mul_scalar_f32(self._ctx.handle, self._dptr, float(alpha), out._dptr, self._host.size))
@@ -332,6 +406,8 @@ class DeviceArray:
         """lib.rs:303-353: shapes must match (ShapeMismatch :304-306), both arrays on the same device."""
         if self._shape != other._shape:
             raise GpuError.shape_mismatch("add_auto: shapes differ")
+        if self._device == Device.Cpu and other._device == Device.Cpu:
+            return self._host_result(self._host + other._host)
         self._need_cuda("add_auto")
         other._need_cuda("add_auto")
         out = self._new_like()

@@ -47,7 +47,7 @@ def _prep(x2):
         xt, ld = G._torch_matrix(x2)
         return True, xt, xt.data_ptr(), ld, xt.shape[0], xt.shape[1], G.torch_context(xt)
     a = G._host_matrix(x2)
-    return False, a, _ptr(a), max(a.shape[1], 1), a.shape[0], a.shape[1], G.default_context(0)
+    return False, a, _ptr(a), max(a.shape[1], 1), a.shape[0], a.shape[1], G.default_context()
 
 
 def _alloc_like(dev, ref, batch, n_out):
@@ -278,6 +278,12 @@ def filtfilt(b, a, x, padtype="odd", padlen=None, *, ctx=None):
     if padtype not in _PAD:
         raise ValueError(f"Unknown value '{padtype}' given to padtype.")       # :4795-4797
     bt = _taps_f32(b) / np.float32(a[0])
+    if padlen is not None:
+        if int(padlen) != padlen:
+            raise ValueError("padlen must be an integer or None")
+        # the ABI's "default 3*ntaps" sentinel is padlen < 0; SciPy's _validate_pad (:4802-4816) takes a negative
+        # padlen as "no extension" (`edge > 0` is false), so that is what a negative value means here too
+        padlen = max(int(padlen), 0)
     return _filtfilt(bt, x, _PAD[padtype], padlen, ctx)
 
 

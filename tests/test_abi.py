@@ -113,10 +113,35 @@ def test_fails_loudly_without_gpu():
     assert L.last_error() != ""
 
 
-def test_device_cpu_is_not_served():
+def test_device_cpu_arm_is_the_crates_own_loop():
+    """lib.rs:517-518: _auto(.., Device::Cpu) is the crate's CPU function.  Asked for explicitly it runs (bit-exact
+    with the reference's loop, pinned here on its known-answer vector lib.rs:1251-1260 and on the oracle); it is
+    never reached from Device.Cuda, which raises without a GPU (test above)."""
     from scir_b200 import gpu
+    x = np.array([[1, 2, 3, 4], [0.5, 0, -0.5, -1]], np.float32)
+    y = gpu.fir1d_batched_f32_auto(x, np.array([0.25, 0.5, 0.25], np.float32), gpu.Device.Cpu)
+    np.testing.assert_allclose(y, [[0.25, 1, 2, 3], [0.125, 0.25, 0, -0.5]], atol=1e-7)
+    rng = np.random.RandomState(3)
+    for n, k in ((1, 1), (5, 9), (300, 31), (1000, 63)):
+        xr = rng.randn(3, n).astype(np.float32)
+        t = rng.randn(k).astype(np.float32)
+        assert np.array_equal(gpu.fir1d_batched_f32(xr, t), O.fir1d_batched_f32(xr, t))
+
+
+def test_out_argument_is_validated():
+    """a wrong-dtype / wrong-shape / strided `out` must be rejected before any pointer is taken."""
+    from scir_b200 import gpu
+    for bad in (np.empty((2, 8), np.float64), np.empty((2, 7), np.float32), np.empty((8, 2), np.float32).T,
+                np.empty((2, 16), np.float32)[:, ::2], [0.0] * 16):
+        with pytest.raises(gpu.GpuError) as e:
+            gpu._check_out_host(bad, (2, 8))
+        assert e.value.kind == "ShapeMismatch"
+    ro = np.empty((2, 8), np.float32)
+    ro.flags.writeable = False
     with pytest.raises(gpu.GpuError):
-        gpu.fir1d_batched_f32_auto(np.ones((1, 4), np.float32), np.ones(2, np.float32), gpu.Device.Cpu)
+        gpu._check_out_host(ro, (2, 8))
+    assert gpu._check_out_host(np.empty((2, 8), np.float32), (2, 8)) == 8
+    assert gpu._check_out_host(np.empty((2, 12), np.float32)[:, :8], (2, 8)) == 12
 
 
 def test_product_never_imports_oracle():

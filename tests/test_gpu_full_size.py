@@ -17,6 +17,7 @@ torch = pytest.importorskip("torch")
 from oracle import oracle as O                      # noqa: E402  (checker only)
 from scir_b200 import gpu, signal                   # noqa: E402
 from bench import CONFIGS, make_taps                # noqa: E402  (the bench's own workload definitions)
+from parity_util import assert_filtfilt_close       # noqa: E402
 
 
 def tol(h, xmax, scale=1.0):
@@ -129,9 +130,11 @@ def test_config5_full_size(padtype):
     xs, ys = x[sel].cpu().numpy(), y[sel].cpu().numpy()
     want = O.filtfilt_fir(b, xs, O.PAD_ODD if padtype == "odd" else O.PAD_NONE, -1)
     hc = np.convolve(b.astype(np.float64), b[::-1].astype(np.float64))
-    assert np.abs(ys - want).max() <= tol(hc, 3.0, 2.0)            # odd extension reaches 3 x max|x|
+    # interior: flat 1e-5 * sum|hc| * max|x| (one fused pass) / 2e-5 * sum|b|^2 * max|x| (two passes); x3 only where
+    # the odd extension is touched (tests/parity_util.py)
+    assert_filtfilt_close(ys, want, b, xs, padtype)
     # zero phase: a symmetric-filtered signal reversed equals the filtered reversed signal (interior)
     yr = signal.filtfilt(b, [1.0], torch.flip(x[:8], dims=[1]).contiguous(), padtype=padtype)
     k = b.size                                                       # FIR: edge rules reach 2(k-1) samples inwards at most
     d = (torch.flip(yr, dims=[1]) - y[:8])[:, 2 * k:n - 2 * k]
-    assert float(d.abs().max()) <= 2 * tol(hc, 3.0, 2.0)
+    assert float(d.abs().max()) <= 2 * tol(hc, 1.0, 2.0)            # two results, each within its own (interior) tolerance

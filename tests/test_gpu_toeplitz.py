@@ -12,6 +12,7 @@ torch = pytest.importorskip("torch")
 
 from oracle import oracle as O                      # noqa: E402  (checker only)
 from scir_b200 import gpu, signal                   # noqa: E402
+from parity_util import assert_filtfilt_close       # noqa: E402
 
 
 def tol(h, x):
@@ -55,6 +56,51 @@ def test_toeplitz_fir_vs_oracle(batch, n, k, terms, loader, split):
     assert ctx.get_option("toeplitz_launches") == t0 + 1          # the tensor-core kernel is the one that ran
     err = np.abs(y - want).max()
     assert err <= tol(taps, x), (err / tol(taps, x), "of tolerance")
+
+
+# BASELINE-shaped cases (firwin taps, U[-1,1) data) with an ASSERTED margin: the default split (block-scaled FP16 x 3)
+# must stay under half the tolerance up to 255 taps and under 0.7 of it at 4097 (where FP32 accumulation over 792 MMAs,
+# not the split, sets the error).  Measured in round 1: 0.05-0.46.  The same fractions are printed by bench.py in every
+# config's `parity` record.
+@pytest.mark.parametrize("k,cutoff,limit", [(63, 0.25, 0.5), (255, 0.2, 0.5), (509, 0.2, 0.5), (1025, 0.05, 0.7), (4097, 0.01, 0.7)])
+@pytest.mark.parametrize("loader", [0, 1])
+def test_toeplitz_firwin_margin(k, cutoff, limit, loader):
+    from scipy.signal import firwin
+    rng = np.random.RandomState(k)
+    b = firwin(k, cutoff).astype(np.float32)
+    x = (rng.rand(4, 1 << 17).astype(np.float32) * 2 - 1)
+    want = O.lfilter_fir(b, x)
+    ctx = toep_ctx(3, loader, 0)
+    y = run(ctx, lambda: signal.lfilter(b, [1.0], dev(x), ctx=ctx)).cpu().numpy()
+    assert ctx.get_option("toeplitz_launches") == 1
+    frac = float(np.abs(y - want).max()) / tol(b, x)
+    assert frac <= limit, (k, frac, "of tolerance; limit", limit)
+
+
+def test_toeplitz_high_dynamic_range_error_model():
+    """the tensor path's error is ABSOLUTE per 16K-sample slab -- <= 3 * 2^-22 * max|slab| * sum|h| -- where the
+    FP32 loop is relative to the local window.  Pin the model: a quiet stretch that shares a slab with a loud burst is
+    accurate to the slab's maximum (the path's stated tolerance, 1e-5 * sum|h| * max|x|), NOT to its own magnitude;
+    a quiet stretch in a slab of its own is accurate to its own magnitude.  include/scir_b200.h states this."""
+    from scipy.signal import firwin
+    rng = np.random.RandomState(99)
+    b = firwin(63, 0.25).astype(np.float32)
+    n = 1 << 16
+    x = (rng.rand(2, n).astype(np.float32) * 2 - 1) * np.float32(1e-6)
+    x[0, 20000:20064] = 1.0                                   # loud burst inside row 0's second slab
+    want = O.lfilter_fir(b, x)
+    ctx = toep_ctx(3, 0, 0)
+    y = run(ctx, lambda: signal.lfilter(b, [1.0], dev(x), ctx=ctx)).cpu().numpy()
+    err = np.abs(y - want)
+    assert err.max() <= tol(b, x)                             # the path's tolerance, relative to max|x| = 1
+    assert err[1].max() <= tol(b, x[1])                       # a uniformly quiet row: relative to ITS max (per-slab scale)
+    assert err[0, :8000].max() <= tol(b, x[1])                # quiet slab of the loud row: still its own scale
+    # the direct FP32 kernel on the same data is relative everywhere (the A/B arm callers can force: long_tap_path=1)
+    d = gpu.Context(0)
+    d.set_option("long_tap_path", 1)
+    yd = run(d, lambda: signal.lfilter(b, [1.0], dev(x), ctx=d)).cpu().numpy()
+    quiet = np.r_[0:19000, 21000:n]
+    assert np.abs(yd[0, quiet] - want[0, quiet]).max() <= tol(b, x[1])
 
 
 def test_toeplitz_error_budget_reported():
@@ -120,11 +166,10 @@ def test_toeplitz_filtfilt_matches_direct_and_oracle(padtype, loader):
     two.set_option("filtfilt_fused", 0)                              # the two-pass form (anticausal kernel path)
     y2 = run(two, lambda: signal.filtfilt(b, [1.0], dev(x), padtype=padtype, ctx=two)).cpu().numpy()
     assert two.get_option("toeplitz_launches") == 2
-    hc = np.convolve(b.astype(np.float64), b[::-1].astype(np.float64))
-    assert np.abs(y - want).max() <= tol(hc, x) * 2
-    assert np.abs(y2 - want).max() <= tol(hc, x) * 2
+    assert_filtfilt_close(y, want, b, x, padtype, what="default")
+    assert_filtfilt_close(y2, want, b, x, padtype, fused=False, what="two-pass")
     yz = run(ctx, lambda: signal.filtfilt_zero_state(b, dev(x), ctx=ctx)).cpu().numpy()
-    assert np.abs(yz - O.filtfilt_fir_nopad(b, x)).max() <= tol(hc, x) * 2
+    assert_filtfilt_close(yz, O.filtfilt_fir_nopad(b, x), b, x, "zero_state")
 
 
 @pytest.mark.parametrize("k", [63, 300, 4097])
