@@ -532,7 +532,8 @@ def measure_e2e(env, cfg, rows, steps, kept):
         p_steps = max(2, min(steps, 5))
         s0 = hctx.get_option("host_staged_calls")
         dtp, rcp = timed(pcall, p_steps, warm=1)
-        okp = bool(rcp == 0 and np.allclose(py[:2], y_head, atol=1e-6) and np.array_equal(py[-1], ay[-1]))
+        # (the pinned and the pageable call may use different row blocks, hence different kernels: compare to tolerance)
+        okp = bool(rcp == 0 and np.allclose(py[:2], y_head, atol=1e-5) and np.allclose(py[rows // 2:], ay[rows // 2:], atol=1e-5))
         e2e["pageable"] = {"value": outs * env.world / dtp / 1e9, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": p_steps,
                            "vs_pinned": dt / dtp, "matches_device_path": okp, "input_is_pinned": int(pin.value),
                            "route": "ctx pinned ring + copy threads" if hctx.get_option("host_staged_calls") > s0 else

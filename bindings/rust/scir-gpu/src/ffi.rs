@@ -96,6 +96,9 @@ extern "C" {
     pub fn scir_b200_resample_poly_f32_host(ctx: *mut ScirB200Ctx, window: *const f32, len_h: i64, up: i64, down: i64, h_x: *const f32, ld_x: i64, batch: i64, n_in: i64, h_y: *mut f32, ld_y: i64) -> c_int;
     pub fn scir_b200_filtfilt_fir_f32(ctx: *mut ScirB200Ctx, b: *const f32, k: i64, pad_mode: c_int, padlen: i64, d_x: *const f32, ld_x: i64, d_y: *mut f32, ld_y: i64, batch: i64, n: i64) -> c_int;
     pub fn scir_b200_filtfilt_fir_f32_host(ctx: *mut ScirB200Ctx, b: *const f32, k: i64, pad_mode: c_int, padlen: i64, h_x: *const f32, ld_x: i64, h_y: *mut f32, ld_y: i64, batch: i64, n: i64) -> c_int;
+    pub fn scir_b200_upfirdn_mode_f64(ctx: *mut ScirB200Ctx, h: *const f64, len_h: i64, up: i64, down: i64, mode: c_int, cval: f64, d_x: *const f64, ld_x: i64, batch: i64, n_in: i64, d_y: *mut f64, ld_y: i64, m_begin: i64, m_count: i64) -> c_int;
+    pub fn scir_b200_resample_poly_pad_f64(ctx: *mut ScirB200Ctx, window: *const f64, len_h: i64, up: i64, down: i64, padtype: c_int, cval: f64, d_x: *const f64, ld_x: i64, batch: i64, n_in: i64, d_y: *mut f64, ld_y: i64) -> c_int;
+    pub fn scir_b200_filtfilt_fir_f64(ctx: *mut ScirB200Ctx, b: *const f64, k: i64, pad_mode: c_int, padlen: i64, d_x: *const f64, ld_x: i64, d_y: *mut f64, ld_y: i64, batch: i64, n: i64) -> c_int;
     pub fn scir_b200_add_scalar_f32(ctx: *mut ScirB200Ctx, d_a: *const f32, alpha: f32, d_y: *mut f32, n: i64) -> c_int;
     pub fn scir_b200_mul_scalar_f32(ctx: *mut ScirB200Ctx, d_a: *const f32, alpha: f32, d_y: *mut f32, n: i64) -> c_int;
     pub fn scir_b200_add_f32(ctx: *mut ScirB200Ctx, d_a: *const f32, d_b: *const f32, d_y: *mut f32, n: i64) -> c_int;

@@ -125,7 +125,71 @@ mod routes {
         })?;
         Array2::from_shape_vec((rows, n), out).map_err(|_| GpuError::ShapeMismatch)
     }
+
+    /// Device scratch for the f64 routes (they take device pointers): RAII around `scir_b200_malloc` / `free`.
+    struct DevBuf(*mut std::os::raw::c_void);
+
+    impl DevBuf {
+        fn new(ctx: &scir_gpu::Context, bytes: usize) -> Result<Self, GpuError> {
+            let mut p = std::ptr::null_mut();
+            check(unsafe { ffi::scir_b200_malloc(ctx.as_ptr(), bytes.max(8), &mut p) })?;
+            Ok(DevBuf(p))
+        }
+    }
+
+    fn run_f64(
+        x: &[f64],
+        n_out_total: usize,
+        f: impl FnOnce(&scir_gpu::Context, *const f64, *mut f64) -> std::os::raw::c_int,
+    ) -> Result<Vec<f64>, GpuError> {
+        let mut out = vec![0.0f64; n_out_total];
+        with_default_context(|ctx| {
+            let dx = DevBuf::new(ctx, x.len() * 8)?;
+            let dy = DevBuf::new(ctx, n_out_total * 8)?;
+            let res = (|| {
+                check(unsafe { ffi::scir_b200_memcpy_h2d(ctx.as_ptr(), dx.0, x.as_ptr() as *const _, x.len() * 8) })?;
+                check(f(ctx, dx.0 as *const f64, dy.0 as *mut f64))?;
+                check(unsafe { ffi::scir_b200_memcpy_d2h(ctx.as_ptr(), out.as_mut_ptr() as *mut _, dy.0, n_out_total * 8) })
+            })();
+            unsafe {
+                ffi::scir_b200_free(ctx.as_ptr(), dx.0);
+                ffi::scir_b200_free(ctx.as_ptr(), dy.0);
+            }
+            res
+        })?;
+        Ok(out)
+    }
+
+    /// f64 twin of the reference's `resample_poly(input: &Array1<f64>, up, down)` (sig/lib.rs:313-362) for ANY rate
+    /// and filter: SciPy's `resample_poly(x, up, down, window=h)` on one f64 row, computed in f64 on the device.
+    pub fn resample_poly_f64(input: &Array1<f64>, up: usize, down: usize, window: &Array1<f64>) -> Result<Array1<f64>, GpuError> {
+        let n = input.len();
+        let mut plan = ffi::ScirB200ResamplePlan::default();
+        check(unsafe { ffi::scir_b200_resample_poly_plan(n as i64, window.len() as i64, up as i64, down as i64, &mut plan) })?;
+        let n_out = if plan.up == 1 && plan.down == 1 { n } else { plan.n_out as usize };
+        let xs = input.as_standard_layout();
+        let ws = window.as_standard_layout();
+        let out = run_f64(xs.as_slice().ok_or(GpuError::ShapeMismatch)?, n_out, |ctx, dx, dy| unsafe {
+            ffi::scir_b200_resample_poly_pad_f64(
+                ctx.as_ptr(), ws.as_ptr(), ws.len() as i64, up as i64, down as i64, ffi::SCIR_B200_EXT_CONSTANT, 0.0, dx,
+                ld(n), 1, n as i64, dy, ld(n_out),
+            )
+        })?;
+        Ok(Array1::from(out))
+    }
+
+    /// f64 zero-phase FIR filtering of one row (the FIR counterpart of the reference's SOS `filtfilt`, sig/lib.rs:278-291).
+    pub fn filtfilt_fir_f64(b: &Array1<f64>, input: &Array1<f64>, pad: PadType, padlen: Option<usize>) -> Result<Array1<f64>, GpuError> {
+        let n = input.len();
+        let xs = input.as_standard_layout();
+        let bs = b.as_standard_layout();
+        let pl = padlen.map(|p| p as i64).unwrap_or(-1);
+        let out = run_f64(xs.as_slice().ok_or(GpuError::ShapeMismatch)?, n, |ctx, dx, dy| unsafe {
+            ffi::scir_b200_filtfilt_fir_f64(ctx.as_ptr(), bs.as_ptr(), bs.len() as i64, pad.code(), pl, dx, ld(n), dy, ld(n), 1, n as i64)
+        })?;
+        Ok(Array1::from(out))
+    }
 }
 
 #[cfg(feature = "cuda")]
-pub use routes::{filtfilt_fir, lfilter_fir, resample_poly, PadType};
+pub use routes::{filtfilt_fir, filtfilt_fir_f64, lfilter_fir, resample_poly, resample_poly_f64, PadType};

@@ -218,6 +218,24 @@ SCIR_B200_API int scir_b200_filtfilt_fir_f32_host(scir_b200_ctx *ctx,
                                     float *h_y, int64_t ld_y,
                                     int64_t batch, int64_t n);
 
+/* ---- f64 twins of the scir-signal routes on device-resident data --------------------------
+ * The reference's own resample_poly / filtfilt are f64 (crates/scir-signal/src/lib.rs:278-291, :313-362) and so are its
+ * fixtures (:638-668); these entry points serve them in f64 (IEEE DFMA), same semantics as the f32 ones above. */
+SCIR_B200_API int scir_b200_upfirdn_mode_f64(scir_b200_ctx *ctx,
+                               const double *h, int64_t len_h, int64_t up, int64_t down, int mode, double cval,
+                               const double *d_x, int64_t ld_x, int64_t batch, int64_t n_in,
+                               double *d_y, int64_t ld_y, int64_t m_begin, int64_t m_count);
+SCIR_B200_API int scir_b200_resample_poly_pad_f64(scir_b200_ctx *ctx,
+                                    const double *window, int64_t len_h, int64_t up, int64_t down,
+                                    int padtype, double cval,
+                                    const double *d_x, int64_t ld_x, int64_t batch, int64_t n_in,
+                                    double *d_y, int64_t ld_y);
+SCIR_B200_API int scir_b200_filtfilt_fir_f64(scir_b200_ctx *ctx,
+                               const double *b, int64_t k, int pad_mode, int64_t padlen,
+                               const double *d_x, int64_t ld_x,
+                               double *d_y, int64_t ld_y,
+                               int64_t batch, int64_t n);
+
 /* ---- DeviceArray<f32> elementwise ops on device-resident data -----------------
  * Replace add_scalar_f32_cuda / mul_scalar_f32_cuda / add_vec_f32_cuda (lib.rs:912-1034, 840-911), the
  * Device::Cuda arms of add_scalar_auto / mul_scalar_auto / add_auto (lib.rs:268-377).  n elements, any

@@ -68,6 +68,9 @@ SIGNATURES = {
     "scir_b200_resample_poly_f32_host": (C.c_int, [vp, fp, i64, i64, i64, fp, i64, i64, i64, fp, i64]),
     "scir_b200_filtfilt_fir_f32": (C.c_int, [vp, fp, i64, C.c_int, i64, fp, i64, fp, i64, i64, i64]),
     "scir_b200_filtfilt_fir_f32_host": (C.c_int, [vp, fp, i64, C.c_int, i64, fp, i64, fp, i64, i64, i64]),
+    "scir_b200_upfirdn_mode_f64": (C.c_int, [vp, vp, i64, i64, i64, C.c_int, C.c_double, vp, i64, i64, i64, vp, i64, i64, i64]),
+    "scir_b200_resample_poly_pad_f64": (C.c_int, [vp, vp, i64, i64, i64, C.c_int, C.c_double, vp, i64, i64, i64, vp, i64]),
+    "scir_b200_filtfilt_fir_f64": (C.c_int, [vp, vp, i64, C.c_int, i64, vp, i64, vp, i64, i64, i64]),
     "scir_b200_add_scalar_f32": (C.c_int, [vp, fp, C.c_float, fp, i64]),
     "scir_b200_mul_scalar_f32": (C.c_int, [vp, fp, C.c_float, fp, i64]),
     "scir_b200_add_f32": (C.c_int, [vp, fp, fp, fp, i64]),

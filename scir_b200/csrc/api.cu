@@ -451,7 +451,7 @@ static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int
         SCIR_CUDA(cudaEventSynchronize(ctx->ev_out[s]), "cudaEventSynchronize(D2H)");
         t_out[s] = ctx->pool->submit_2d(reinterpret_cast<char*>(h_y + b * rows * ld_y), static_cast<size_t>(ld_y) * 4,
                                         static_cast<const char*>(ctx->pin_out[s].ptr), static_cast<size_t>(ldo) * 4,
-                                        static_cast<size_t>(n_out) * 4, static_cast<size_t>(rows_of(b)));
+                                        static_cast<size_t>(n_out) * 4, static_cast<size_t>(rows_of(b)), ctx->opt.host_stage_nt != 0);
         return SCIR_B200_OK;
     };
     auto run_blocks = [&]() -> int {
@@ -464,7 +464,7 @@ static int host_pipeline(scir_b200_ctx* ctx, const float* h_x, int64_t ld_x, int
             if (blk >= S) SCIR_CUDA(cudaEventSynchronize(ctx->ev_in[s]), "cudaEventSynchronize(H2D)");   // slot's last DMA read done
             t_in = ctx->pool->submit_2d(static_cast<char*>(ctx->pin_in[s].ptr), static_cast<size_t>(ldi) * 4,
                                         reinterpret_cast<const char*>(h_x + r0 * ld_x), static_cast<size_t>(ld_x) * 4,
-                                        static_cast<size_t>(n_in) * 4, static_cast<size_t>(nr));
+                                        static_cast<size_t>(n_in) * 4, static_cast<size_t>(nr), ctx->opt.host_stage_nt != 0);
         }
         if (stage_y && blk >= LAG) SCIR_TRY(drain(blk - LAG));
         if (stage_x) ctx->pool->wait(t_in);
@@ -676,6 +676,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "host_stage")) return &o.host_stage;
     if (!strcmp(key, "host_copy_threads")) return &o.host_copy_threads;
     if (!strcmp(key, "host_stage_wc")) return &o.host_stage_wc;
+    if (!strcmp(key, "host_stage_nt")) return &o.host_stage_nt;
     return nullptr;
 }
 

@@ -76,6 +76,7 @@ struct Options {
                                  // 2 cudaHostRegister the caller's spans for the duration of the call
     int64_t host_copy_threads = 0;   // copy threads of the pinned ring (0 = auto: min(8, hardware threads / 2))
     int64_t host_stage_wc = 0;   // 1: the H2D half of the pinned ring is write-combined memory
+    int64_t host_stage_nt = 1;   // 1: the copy threads use non-temporal stores (no read-for-ownership); 0: plain memcpy (A/B)
 };
 
 class CopyPool;                 // copy_pool.hpp
@@ -151,6 +152,19 @@ struct FirPass {
     int dir;
 };
 
+struct FirPass64 {            // the same pass on f64 rows (fir_f64.cu)
+    const double* x;
+    double* y;
+    long long ld_x, ld_y;
+    long long batch;
+    long long n_x, n_v;
+    long long in_off, out_off;
+    long long out_begin, out_end;
+    int ext_mode;
+    int bound;
+    int dir;
+};
+
 // c: coefficients by delay index (lfilter order), length k.
 // launch_fir picks the kernel (tcgen05 Toeplitz vs FP32 direct) from the ctx options; launch_fir_pass
 // is the FP32 direct family.
@@ -178,6 +192,7 @@ int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down)
 // ---- f64 twin of the hot path (fir_f64.cu); taps by delay index, host pointer -----------------------------
 int launch_fir_f64(scir_b200_ctx* ctx, const double* d_x, int64_t ld_x, const double* taps_by_delay, int64_t k, double* d_y,
                    int64_t ld_y, int64_t batch, int64_t n);
+int launch_fir_pass_f64(scir_b200_ctx* ctx, const FirPass64& pass, const double* taps_by_delay, int64_t k);
 
 // ---- DeviceArray elementwise ops (elementwise.cu): op 0 add-scalar, 1 mul-scalar, 2 add ------------------
 int launch_elementwise(scir_b200_ctx* ctx, int op, const float* d_a, const float* d_b, float alpha, float* d_y, int64_t n);

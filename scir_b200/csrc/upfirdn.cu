@@ -6,7 +6,7 @@
 // i.e. the zero-stuffed samples the reference's legacy resampler multiplies by
 // (crates/scir-signal/src/lib.rs:348-352) are never touched.
 #include "common.cuh"
-#include "upfirdn_ext.cuh"
+#include "ext_modes.cuh"
 
 #include <algorithm>
 

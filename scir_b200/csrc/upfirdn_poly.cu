@@ -24,7 +24,7 @@
 
 #include <memory>
 #include "ptx.cuh"
-#include "upfirdn_ext.cuh"
+#include "ext_modes.cuh"
 
 #include <algorithm>
 

@@ -41,8 +41,14 @@ def fir1d_batched_f32_sharded(x_local, taps, **kw):
     return gpu.fir1d_batched_f32_cuda(x_local, taps, **kw)
 
 
-def gather_rows(y_local, batch: int, group=None):
-    """All-gather the row blocks back into the full (batch, n) array on every rank (opt-in)."""
+def gather_rows(y_local, batch: int, group=None, dst: int | None = None):
+    """The OPTIONAL collective of the path (north_star (d)): put the row blocks back together.
+
+    dst=None: all-gather -- every rank gets the full (batch, n) array.
+    dst=r:    gather to ONE rank ("the caller requests the output on one device"): rank r returns the full array,
+              every other rank returns None.  Over NCCL this is send/recv fan-in across NVLink; it moves
+              (world-1)/world of the output once, where the all-gather moves it world-1 times.
+    Never on the timed hot path: filtering needs no communication at all."""
     import torch
     import torch.distributed as dist
     world, rank = world_rank(group)
@@ -50,9 +56,25 @@ def gather_rows(y_local, batch: int, group=None):
         return y_local
     n = y_local.shape[1]
     blocks = [shard_rows(batch, world, r) for r in range(world)]
-    cap = max(b - a for a, b in blocks)
-    padded = torch.zeros((cap, n), dtype=y_local.dtype, device=y_local.device)
-    padded[: y_local.shape[0]] = y_local
-    buf = torch.empty((world * cap, n), dtype=y_local.dtype, device=y_local.device)
-    dist.all_gather_into_tensor(buf, padded, group=group)
-    return torch.cat([buf[r * cap: r * cap + (b - a)] for r, (a, b) in enumerate(blocks)], dim=0)
+    if dst is None:
+        cap = max(b - a for a, b in blocks)
+        padded = torch.zeros((cap, n), dtype=y_local.dtype, device=y_local.device)
+        padded[: y_local.shape[0]] = y_local
+        buf = torch.empty((world * cap, n), dtype=y_local.dtype, device=y_local.device)
+        dist.all_gather_into_tensor(buf, padded, group=group)
+        return torch.cat([buf[r * cap: r * cap + (b - a)] for r, (a, b) in enumerate(blocks)], dim=0)
+    if not 0 <= dst < world:
+        raise ValueError(f"dst rank {dst} outside the group of {world}")
+    # uneven shards: point-to-point fan-in straight into the destination's rows (no padding, no extra copy)
+    if rank == dst:
+        full = torch.empty((batch, n), dtype=y_local.dtype, device=y_local.device)
+        a, b = blocks[rank]
+        full[a:b] = y_local
+        reqs = [dist.irecv(full[blocks[r][0]: blocks[r][1]], src=dist.get_global_rank(group, r) if group else r, group=group)
+                for r in range(world) if r != dst and blocks[r][1] > blocks[r][0]]
+        for q in reqs:
+            q.wait()
+        return full
+    if y_local.shape[0] > 0:
+        dist.isend(y_local.contiguous(), dst=dist.get_global_rank(group, dst) if group else dst, group=group).wait()
+    return None

@@ -291,3 +291,131 @@ def filtfilt_zero_state(b, x, *, ctx=None):
     """The reference's filtfilt structure (sig/lib.rs:278-291) with an FIR numerator: zero-state
     forward pass, zero-state pass over the reversed result, reverse.  No padding."""
     return _filtfilt(b, x, L.PAD_ZERO_STATE, None, ctx)
+
+
+# ---- f64 twins (SURVEY.md 8(f).4) ------------------------------------------------------------------------------
+# The reference's own `resample_poly` and `filtfilt` take and return Array1<f64> (sig/lib.rs:278-291, :313-362) and its
+# fixtures are f64 (:638-668).  These functions serve float64 rows in float64 on the device (IEEE DFMA kernels,
+# scir_b200/csrc/f64_routes.cu, fir_f64.cu) instead of down-casting them to the f32 path.  Inputs: float64 numpy arrays
+# (uploaded / downloaded around the device call) or float64 CUDA tensors (device-resident).
+def _as_2d_f64(x):
+    if _is_torch(x):
+        import torch
+        if x.dtype != torch.float64 or not x.is_cuda:
+            raise GpuError.shape_mismatch("device input must be a float64 CUDA tensor")
+        x2, was1d = (x[None, :], True) if x.dim() == 1 else (x, False)
+        if x2.dim() != 2:
+            raise GpuError.shape_mismatch("x must be 1-D or 2-D")
+        return x2.contiguous(), was1d
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    if a.ndim not in (1, 2):
+        raise GpuError.shape_mismatch("x must be 1-D or 2-D")
+    return (a[None, :], True) if a.ndim == 1 else (a, False)
+
+
+def _run_f64(x2, n_out, ctx, call):
+    """call(ctx, x_ptr, ld_x, y_ptr, ld_y) -> rc on device pointers; handles numpy <-> device staging."""
+    batch, n = x2.shape
+    if _is_torch(x2):
+        import torch
+        c = ctx or G.torch_context(x2)
+        y = torch.empty((batch, n_out), dtype=torch.float64, device=x2.device)
+        rc = call(c, x2.data_ptr(), max(n, 1), y.data_ptr(), max(n_out, 1))
+        return y, rc
+    c = ctx or G.default_context()
+    y = np.empty((batch, n_out), dtype=np.float64)
+    bx, by = _DevBuf(c, x2.nbytes).upload(x2), _DevBuf(c, y.nbytes)
+    try:
+        rc = call(c, bx.p, max(n, 1), by.p, max(n_out, 1))
+        if rc == L.OK:
+            c.sync()
+            by.download(y)
+    finally:
+        bx.free()
+        by.free()
+    return y, rc
+
+
+def _taps_f64(t) -> np.ndarray:
+    if _is_torch(t):
+        t = t.detach().cpu().numpy()
+    a = np.ascontiguousarray(t, dtype=np.float64)
+    if a.ndim != 1 or a.size < 1:
+        raise GpuError.shape_mismatch("taps must be 1-D with at least one element")
+    return a
+
+
+def upfirdn_f64(h, x, up=1, down=1, mode="constant", cval=0.0, *, ctx=None):
+    """upfirdn(h, x, up, down, mode, cval) on float64 rows (scipy/signal/_upfirdn.py:107-216)."""
+    if int(up) != up or int(down) != down:
+        raise ValueError("up and down must be integers")
+    up, down = int(up), int(down)
+    if up < 1 or down < 1:
+        raise ValueError("Both up and down must be >= 1")
+    m = _mode_code(mode)
+    ht = _taps_f64(h)
+    x2, was1d = _as_2d_f64(x)
+    n = x2.shape[1]
+    if n < 1:
+        raise ValueError("x must have at least one sample")
+    lo = upfirdn_output_len(ht.size, n, up, down)
+    y, rc = _run_f64(x2, lo, ctx, lambda c, xp, ldx, yp, ldy: _load().scir_b200_upfirdn_mode_f64(
+        c.handle, _ptr(ht), ht.size, up, down, m, float(cval), xp, ldx, x2.shape[0], n, yp, ldy, 0, lo))
+    _check(rc)
+    return y[0] if was1d else y
+
+
+def resample_poly_f64(x, up, down, window=("kaiser", 5.0), padtype="constant", cval=None, *, ctx=None):
+    """resample_poly on float64 rows (scipy/signal/_signaltools.py:3865-3957), every padtype.  With the reference's
+    31 legacy taps / 2 as `window` and (up, down) = (2, 3) this is scir_signal::resample_poly (sig/lib.rs:313-362)."""
+    if int(up) != up or int(down) != down:
+        raise ValueError("up and down must be integers")
+    up, down = int(up), int(down)
+    if up < 1 or down < 1:
+        raise ValueError("up and down must be >= 1")
+    if cval is not None and padtype != "constant":
+        raise ValueError("cval has no effect when padtype is " + str(padtype))
+    if padtype in _PAD_STATS:
+        code = _PAD_STATS[padtype]
+    elif padtype in UPFIRDN_MODES:
+        code = UPFIRDN_MODES[padtype]
+    else:
+        raise ValueError("padtype must be one of: " + ", ".join(list(UPFIRDN_MODES) + list(_PAD_STATS)))
+    if isinstance(window, (tuple, str)):
+        if window != ("kaiser", 5.0):
+            raise GpuError.backend_unavailable("pass the filter as an array; only the default ('kaiser', 5.0) design is built in")
+        window = kaiser_lowpass(up, down)
+    w = _taps_f64(window)
+    x2, was1d = _as_2d_f64(x)
+    n = x2.shape[1]
+    plan = resample_poly_plan(n, w.size, up, down)
+    n_out = n if (plan["up"] == 1 and plan["down"] == 1) else plan["n_out"]
+    y, rc = _run_f64(x2, n_out, ctx, lambda c, xp, ldx, yp, ldy: _load().scir_b200_resample_poly_pad_f64(
+        c.handle, _ptr(w), w.size, up, down, code, float(cval or 0.0), xp, ldx, x2.shape[0], n, yp, ldy))
+    _check(rc)
+    return y[0] if was1d else y
+
+
+def filtfilt_f64(b, a, x, padtype="odd", padlen=None, *, ctx=None):
+    """filtfilt(b, [a0], x, padtype, padlen), method='pad', on float64 rows (_signaltools.py:4745-4826).
+    padtype='zero_state' is the reference's own structure (sig/lib.rs:278-291) with an FIR numerator."""
+    a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+    if a.size != 1:
+        raise GpuError.backend_unavailable("only FIR numerators (a = [a0]) run on this path")
+    if padtype == "zero_state":
+        mode = L.PAD_ZERO_STATE
+    elif padtype in _PAD:
+        mode = _PAD[padtype]
+    else:
+        raise ValueError(f"Unknown value '{padtype}' given to padtype.")
+    bt = _taps_f64(b) / a[0]
+    if padlen is not None:
+        padlen = max(int(padlen), 0)
+    x2, was1d = _as_2d_f64(x)
+    n = x2.shape[1]
+    y, rc = _run_f64(x2, n, ctx, lambda c, xp, ldx, yp, ldy: _load().scir_b200_filtfilt_fir_f64(
+        c.handle, _ptr(bt), bt.size, mode, -1 if padlen is None else padlen, xp, ldx, yp, ldy, x2.shape[0], n))
+    if rc == L.ERR_SHAPE:
+        raise ValueError(L.last_error())
+    _check(rc)
+    return y[0] if was1d else y

@@ -85,10 +85,13 @@ int main(int argc, char** argv)
         // elementwise _auto ops: the reference's doc-test vectors (lib.rs:258-262, :293-298, :345-350), chained on the device
         gpu::DeviceArray da = gpu::DeviceArray::from_cpu_slice({3}, gpu::DType::F32, {1.0f, 2.0f, 3.0f});
         gpu::DeviceArray db = gpu::DeviceArray::from_cpu_slice({3}, gpu::DType::F32, {0.5f, 1.5f, 2.5f});
-        bool cpu_threw = false;
-        try { (void)da.add_scalar_auto(1.0f); } catch (const gpu::GpuError&) { cpu_threw = true; }
-        EXPECT(cpu_threw);                                      // no CPU path in this backend
+        // a Device::Cpu array runs the crate's own loop (lib.rs:206-221) and stays on the CPU; mixed devices are an error
+        const gpu::DeviceArray dcpu = da.add_scalar_auto(1.0f);
+        EXPECT(dcpu.device() == gpu::Device::Cpu && dcpu.to_cpu_vec() == (std::vector<float>{2.0f, 3.0f, 4.0f}));
         da.to_device(gpu::Device::Cuda);
+        bool mixed_threw = false;
+        try { (void)da.add_auto(db); } catch (const gpu::GpuError&) { mixed_threw = true; }
+        EXPECT(mixed_threw);
         db.to_device(gpu::Device::Cuda);
         EXPECT(da.add_scalar_auto(1.0f).to_cpu_vec() == (std::vector<float>{2.0f, 3.0f, 4.0f}));
         EXPECT(da.mul_scalar_auto(2.0f).to_cpu_vec() == (std::vector<float>{2.0f, 4.0f, 6.0f}));

@@ -39,7 +39,12 @@ def _worker(rank, world, port, batch, n, k, q):
         yl = torch.from_numpy(O.fir1d_batched_f32(xl.numpy(), taps)) if xl.shape[0] else torch.zeros((0, n))
         y = sdist.gather_rows(yl, batch)
         want = O.fir1d_batched_f32(x, taps)
-        q.put((rank, bool(np.array_equal(y.numpy(), want)), (r0, r1)))
+        ok = bool(np.array_equal(y.numpy(), want))
+        # gather to ONE rank (north_star (d): "when the caller requests the output on one device")
+        for dst in range(world):
+            y1 = sdist.gather_rows(yl, batch, dst=dst)
+            ok = ok and ((y1 is None) if rank != dst else bool(np.array_equal(y1.numpy(), want)))
+        q.put((rank, ok, (r0, r1)))
     finally:
         dist.destroy_process_group()
 

@@ -776,8 +776,11 @@ def test_device_array_elementwise_ops_bit_exact():
         a.add_auto(c)
     assert ei.value.kind == "ShapeMismatch"
     cpu = gpu.DeviceArray.from_cpu_slice([3], gpu.DType.F32, [1.0, 2.0, 3.0])
-    with pytest.raises(gpu.GpuError):                       # no CPU path in this backend
-        cpu.add_scalar_auto(1.0)
+    # a Device.Cpu array runs the crate's own loop (lib.rs:206-221) and stays on the CPU; the array's device decides
+    r = cpu.add_scalar_auto(1.0)
+    assert r.device() == Device.Cpu and r.to_cpu_vec() == [2.0, 3.0, 4.0]
+    with pytest.raises(gpu.GpuError):                       # operands on different devices: never silently moved
+        a.add_auto(cpu)
     rng = np.random.RandomState(9)
     for n in (1, 3, 4, 1023, 4096 * 4 * 4 + 5, 3_000_001):
         x = (rng.randn(n) * 10).astype(np.float32)

@@ -42,17 +42,16 @@ print("cpu", d.get("cpu_baseline"))
 PY
 }
 if has bench; then
-  /usr/bin/time -v -o $OUT/bench_time.txt timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -3 $OUT/bench.err
-  grep -E "Elapsed|Maximum resident" $OUT/bench_time.txt
+  SECONDS=0; timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -3 $OUT/bench.err
+  echo "bench wall: $SECONDS s"
   summ $OUT/bench.json
 fi
 if has ref; then
-  /usr/bin/time -v -o $OUT/ref_time.txt timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"
-  grep -E "Elapsed" $OUT/ref_time.txt; cut -c1-600 $OUT/bench_ref.json
+  SECONDS=0; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"
+  echo "ref wall: $SECONDS s"; cut -c1-600 $OUT/bench_ref.json
 fi
 if has pageable; then
-  for spec in "host_copy_threads=2" "host_copy_threads=4" "host_copy_threads=6" "host_copy_threads=12" "host_copy_threads=8 host_stage_wc=1" \
-              "host_copy_threads=8 host_block_rows=1" "host_copy_threads=8 host_block_rows=4" "host_copy_threads=8 host_block_rows=8" "host_stage=0" "host_stage=2"; do
+  for spec in ${PAGEABLE_SPECS:-"host_stage_nt=1" "host_stage_nt=0" "host_copy_threads=4" "host_copy_threads=12" "host_block_rows=4" "host_block_rows=1" "host_stage_wc=1"}; do
     o=""; tag=""; for kv in $spec; do o="$o --opt $kv"; tag="${tag}_${kv%%=*}${kv#*=}"; done
     timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-sweep $o > $OUT/benchP$tag.json 2> $OUT/benchP$tag.err
     python -c "
