@@ -69,7 +69,8 @@ struct Options {
     int64_t toeplitz_loader = 0; // 0 auto (TMA-fed in-place buffers when they fit); 1 force the register-prefetch loader
     int64_t toeplitz_min_k = 1024; // auto mode: tap counts from here on always take the tensor path
     int64_t toeplitz_min_k_full = 2;  // auto mode: ... and from here on when the cost model (api.cu: prefer_toeplitz) says so
-    int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel
+    int64_t upfirdn_variant = 0; // 0 auto; 1 force generic polyphase kernel (others: upfirdn_poly.cu launch_one)
+    int64_t upfirdn_ws_stages = 3; // input stages of the warp-specialised polyphase kernel: 3 (2 CTAs/SM) or 2 (3 CTAs/SM)
     // *_host entry points, when the caller's arrays are PAGEABLE (a Rust Vec / ndarray / numpy buffer):
     int64_t host_stage = 1;      // 1 stage through the ctx's pinned ring with copy threads (default); 0 hand the pageable
                                  // pointer to cudaMemcpyAsync (driver-staged, host-synchronous: the A/B arm);

@@ -87,6 +87,61 @@ struct PolyGeom {
                 if (tap_of(2 * p, s) >= 0 || tap_of(2 * p + 1, s) >= 0) ++n;
         return n;
     }
+    // ---- tap-reuse form (poly_core3) ---------------------------------------------------------------------------
+    // Output pairs p and p + PP apply the SAME tap pair, SH samples further on: the phase pattern of a pair repeats
+    // every 2*UP outputs (UP odd) or every UP outputs (UP even).  So one uniform-register tap pair feeds up to GP
+    // FFMA2s instead of one, and the table holds only the pairs of the first period.
+    static constexpr int NPAIR = R / 2;
+    static constexpr int PP = (UP % 2 == 1) ? UP : UP / 2;
+    static constexpr int SH = (UP % 2 == 1) ? 2 * DOWN : DOWN;
+    static constexpr int GP = (NPAIR + PP - 1) / PP;
+    static constexpr int LA = SH * (GP - 1);                   // furthest sample a period-0 pair's tap reaches ahead
+    __host__ __device__ static constexpr bool pair_live(int p0, int s)
+    {
+        return p0 < NPAIR && (tap_of(2 * p0, s) >= 0 || tap_of(2 * p0 + 1, s) >= 0);
+    }
+    __host__ __device__ static constexpr int pair_count3()
+    {
+        int n = 0;
+        for (int s = 0; s < 4 * W4; ++s)
+            for (int p0 = 0; p0 < PP; ++p0)
+                if (pair_live(p0, s)) ++n;
+        return n;
+    }
+    // shift invariance the reuse rests on, and the window bound of the furthest reuse (checked at compile time)
+    __host__ __device__ static constexpr bool reuse_ok()
+    {
+        for (int s = 0; s < 4 * W4; ++s)
+            for (int p0 = 0; p0 < PP; ++p0)
+                for (int g = 1; g < GP; ++g) {
+                    const int p = p0 + g * PP;
+                    if (p >= NPAIR) continue;
+                    const int s2 = s + g * SH;
+                    const int a = tap_of(2 * p0, s), b = tap_of(2 * p0 + 1, s);
+                    if (s2 >= 4 * W4) {
+                        if (a >= 0 || b >= 0) return false;
+                        continue;
+                    }
+                    if (tap_of(2 * p, s2) != a || tap_of(2 * p + 1, s2) != b) return false;
+                }
+        // and no live (pair, sample) of a later period is missed: its period-0 image must exist inside the window
+        for (int s2 = 0; s2 < 4 * W4; ++s2)
+            for (int p = PP; p < NPAIR; ++p) {
+                const int g = p / PP, s = s2 - g * SH;
+                if ((tap_of(2 * p, s2) >= 0 || tap_of(2 * p + 1, s2) >= 0) && s < 0) return false;
+            }
+        return true;
+    }
+    static void fill_pairs3(const float* c, PolyPairs* out)    // host: same enumeration order as poly_core3
+    {
+        int n = 0;
+        for (int s = 0; s < 4 * W4; ++s)
+            for (int p0 = 0; p0 < PP; ++p0)
+                if (pair_live(p0, s)) {
+                    const int a = tap_of(2 * p0, s), b = tap_of(2 * p0 + 1, s);
+                    out->p[n++] = make_float2(a >= 0 ? c[a] : 0.f, b >= 0 ? c[b] : 0.f);
+                }
+    }
     static void fill_pairs(const float* c, PolyPairs* out)     // host: same enumeration order as poly_core2
     {
         int n = 0;
@@ -139,6 +194,66 @@ __device__ __forceinline__ void poly_core2(float (&acc)[UP * G], const float* wb
     }
 #pragma unroll
     for (int p = 0; p < R / 2; ++p)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * p]), "=f"(acc[2 * p + 1]) : "l"(acc2[p]));
+    if constexpr (R % 2 == 1) acc[R - 1] = tail;
+}
+
+// Same arithmetic as poly_core2 -- the same (output pair, sample) FFMA2s with the same taps -- but ordered so that a
+// tap pair is loaded ONCE (one LDCU.64) and applied to every output pair that shares it: pairs p0, p0+PP, p0+2PP, ...
+// at samples s, s+SH, s+2SH, ...  poly_core2 spends one LDCU.64 per FFMA2 (ncu, config 4: LDCU = 28 % of all issued
+// instructions, one for every 1.9 FFMA2); here it is one per GP FFMA2 (config 4: GP = 5).  The sample window is
+// pulled through registers by LDS.128 just ahead of its first use (LA samples of look-ahead), so the live window is
+// ~LA + 8 registers instead of the whole tile row.
+template <int UP, int DOWN, int G, int KCP, int Z>
+__device__ __forceinline__ void poly_core3(float (&acc)[UP * G], const float* wbase, const PolyTaps& taps, const PolyPairs& pairs)
+{
+    using Geo = PolyGeom<UP, DOWN, G, KCP, Z>;
+    constexpr int R = Geo::R, W4 = Geo::W4, PP = Geo::PP, SH = Geo::SH, GP = Geo::GP, NPAIR = Geo::NPAIR;
+    static_assert(Geo::pair_count3() <= kPolyMaxPairs, "pair table too small");
+    static_assert(Geo::reuse_ok(), "tap pairs are not shift-invariant across periods for this geometry");
+    constexpr int LA4 = (Geo::LA + 3) / 4 + 1;                     // float4s kept loaded ahead of the current one
+    unsigned long long acc2[NPAIR > 0 ? NPAIR : 1];
+    float tail = 0.f;                                              // odd R: the last output stays scalar
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) acc2[p] = 0ull;
+    const float4* w = reinterpret_cast<const float4*>(wbase - KCP - Geo::ZP);
+    float xw[4 * W4];                                              // static indices only: lives in registers
+#pragma unroll
+    for (int v4 = 0; v4 < W4; ++v4) {
+        if (v4 < LA4) {
+            const float4 v = w[v4];
+            xw[4 * v4] = v.x; xw[4 * v4 + 1] = v.y; xw[4 * v4 + 2] = v.z; xw[4 * v4 + 3] = v.w;
+        }
+    }
+    int cnt = 0;                                                   // compile-time after unrolling
+#pragma unroll
+    for (int b = 0; b < W4; ++b) {
+        if (b + LA4 < W4) {
+            const float4 v = w[b + LA4];
+            xw[4 * (b + LA4)] = v.x; xw[4 * (b + LA4) + 1] = v.y; xw[4 * (b + LA4) + 2] = v.z; xw[4 * (b + LA4) + 3] = v.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int s = 4 * b + e;
+#pragma unroll
+            for (int p0 = 0; p0 < PP; ++p0) {
+                if (Geo::pair_live(p0, s)) {
+                    const float2 tp = pairs.p[cnt];
+                    ++cnt;
+#pragma unroll
+                    for (int g = 0; g < GP; ++g) {
+                        if (p0 + g * PP < NPAIR && s + g * SH < 4 * W4) fma2_bcast(acc2[p0 + g * PP], xw[s + g * SH], tp);
+                    }
+                }
+            }
+            if constexpr (R % 2 == 1) {
+                const int a = Geo::tap_of(R - 1, s);
+                if (a >= 0) tail = fmaf(taps.c[a], xw[s], tail);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p)
         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * p]), "=f"(acc[2 * p + 1]) : "l"(acc2[p]));
     if constexpr (R % 2 == 1) acc[R - 1] = tail;
 }
@@ -364,7 +479,8 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
 
         float acc[R];
         if constexpr (NCH == 1) {
-            if (packed) poly_core2<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
+            if (packed == 2) poly_core3<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
+            else if (packed) poly_core2<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
             else poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, in + HALO + tid * SIN, nchunk, taps);
         } else {
             poly_core<UP, DOWN, G, KCP, Z, NCH>(acc, in + HALO + tid * SIN, nchunk, taps);
@@ -392,6 +508,126 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
         advance(nrow, ntile);
     }
     if (tid == 0) bulk_store_wait_read<0>();               // smem must outlive the last store's read
+}
+
+// ---- the warp-specialised kernel (default for single-chunk filters) -------------------------------------------
+// Same tiles and the same arithmetic as upfirdn_stream_kernel, but NO CTA barrier in the steady state:
+//   * warp 8 is the producer: one lane keeps kWsStages input stages filled by cp.async.bulk (`full` mbarriers carry
+//     the byte count, `empty` mbarriers are arrived on by the 8 compute warps when they are done with a stage);
+//     edge tiles, whose samples come from the extension mode, are synthesised by the producer's 32 lanes;
+//   * warps 0-7 compute (poly_core3: one tap-pair load per GP FFMA2s) and each drains ITS 32*R outputs with its own
+//     bulk store from its own slice of the output buffer -- so a fast warp never waits for a slow one, and the only
+//     things a compute warp ever waits for are its input stage and its own previous store.
+// What the streaming kernel lost (ncu, config 4: 0.66 barrier stalls per issue, 29 % of the warp slots idle, loads
+// and stores parked behind two __syncthreads per tile) is what this removes.
+constexpr int kWsThreads = kPolyNT + 32;
+
+template <int UP, int DOWN, int G, int KCP, int Z, int kWsStages>
+__global__ void __launch_bounds__(kWsThreads, (kWsStages >= 3) ? 2 : 3)
+upfirdn_ws_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps, long long batch,
+                  const __grid_constant__ PolyPairs pairs)
+{
+    constexpr int NT = kPolyNT;
+    constexpr int R = UP * G;
+    constexpr int SIN = DOWN * G;
+    static_assert(SIN % 4 == 0 && (SIN / 4) % 2 == 1, "dense tile must be conflict-free for LDS.128");
+    constexpr int TILE_OUT = NT * R;
+    constexpr int TILE_IN = NT * SIN;
+    constexpr int ZP = (Z > 0) ? 4 : 0;
+    constexpr int HALO = KCP + ZP;
+    constexpr int LEN = HALO + TILE_IN + 4;
+    constexpr int WOUT = 32 * R;                          // outputs of one compute warp
+    static_assert(LEN % 4 == 0 && (WOUT * 4) % 16 == 0, "16-byte bulk copies");
+
+    extern __shared__ __align__(128) float smem[];        // in[0..kWsStages) | out
+    __shared__ __align__(8) unsigned long long bars[2 * kWsStages];     // full[s], empty[s]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* const out_s = smem + kWsStages * LEN;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kWsStages]);
+    const long long GD = gridDim.x;
+    const long long step_row = GD / q.ntiles, step_tile = GD - step_row * q.ntiles;
+    long long row = blockIdx.x / q.ntiles, tile = blockIdx.x - row * q.ntiles;
+    auto advance = [&](long long& r, long long& t) {
+        r += step_row;
+        t += step_tile;
+        if (t >= q.ntiles) {
+            t -= q.ntiles;
+            r += 1;
+        }
+    };
+    auto first_sample = [&](long long t) {
+        const long long m0 = q.base_m + t * TILE_OUT;
+        return (m0 / UP) * DOWN - HALO;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kWsStages; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, NT / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();                                       // the only CTA barrier: mbarrier init is visible
+
+    if (warp == NT / 32) {
+        // ---------------- producer ----------------
+        for (int it = 0; row < batch; ++it) {
+            const int s = it % kWsStages;
+            const uint32_t k = static_cast<uint32_t>(it / kWsStages);
+            if (k > 0) mbar_wait(empty0 + 8u * s, (k - 1) & 1u);       // the stage's previous tile has been consumed
+            const long long a = first_sample(tile);
+            const float* __restrict__ xr = q.x + row * q.ld_x;
+            float* const in = smem + s * LEN;
+            if (q.in_vec_ok && a >= 0 && a + LEN <= q.n_in) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(full0 + 8u * s, LEN * 4u);
+                    bulk_copy_g2s(smem_u32(in), xr + a, LEN * 4u, full0 + 8u * s);
+                }
+            } else {                                       // edge tile: samples outside the row by extension mode
+                for (int t = lane; t < LEN; t += 32) in[t] = upfirdn_sample(xr, a + t, q.n_in, q.ext);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8u * s);
+            }
+            advance(row, tile);
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    float* const my_out = out_s + warp * WOUT;
+    for (int it = 0; row < batch; ++it) {
+        const int s = it % kWsStages;
+        const uint32_t k = static_cast<uint32_t>(it / kWsStages);
+        const long long m0 = q.base_m + tile * TILE_OUT + static_cast<long long>(warp) * WOUT;     // this warp's first output
+        float* __restrict__ yr = q.y + row * q.ld_y;
+        const float* const in = smem + s * LEN;
+
+        mbar_wait(full0 + 8u * s, k & 1u);
+        float acc[R];
+        poly_core3<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
+        __syncwarp();                                      // every lane's reads of the stage are done
+        if (lane == 0) {
+            mbar_arrive(empty0 + 8u * s);
+            bulk_store_wait_read<0>();                     // this warp's previous store has drained its slice
+        }
+        __syncwarp();
+        poly_store_acc<R>(my_out + lane * R, acc);
+        if (q.out_vec_ok && m0 >= q.m_begin && m0 + WOUT <= q.m_end) {
+            fence_proxy_async_smem();                      // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) bulk_copy_s2g(yr + (m0 - q.m_begin), smem_u32(my_out), WOUT * 4u);
+        } else {
+            __syncwarp();
+            for (int t = lane; t < WOUT; t += 32) {
+                const long long m = m0 + t;
+                if (m >= q.m_begin && m < q.m_end) yr[m - q.m_begin] = my_out[t];
+            }
+            __syncwarp();                                  // the slice is rewritten by the next tile
+        }
+        advance(row, tile);
+    }
+    if (lane == 0) bulk_store_wait_read<0>();              // smem must outlive the last store's read
 }
 
 // ---- the warp-pipelined kernel (A/B: upfirdn_variant = 6) -------------------------------------------------
@@ -514,10 +750,39 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
     thread_local std::unique_ptr<PolyPairs> pairs_owner;    // freed when the thread exits
     if (!pairs_owner) pairs_owner.reset(new PolyPairs());
     PolyPairs* pairs = pairs_owner.get();
-    // upfirdn_variant: 0 auto (streaming, FFMA2) | 3 one tile per CTA (FFMA2) | 4 streaming, scalar FFMA | 5 tile, scalar FFMA
-    const int packed = (NCH == 1 && ctx->opt.upfirdn_variant != 4 && ctx->opt.upfirdn_variant != 5) ? 1 : 0;   // 6: warp-pipelined (FFMA2)
-    if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
+    // upfirdn_variant: 0 auto (warp-specialised, tap-reuse FFMA2 core) | 7 streaming + tap-reuse core | 8 streaming + one tap-pair
+    // load per FFMA2 (the round-1 default) | 3 one tile per CTA (FFMA2) | 4 streaming, scalar FFMA | 5 tile, scalar FFMA |
+    // 6 per-warp pipelines (FFMA2)
+    const int v = static_cast<int>(ctx->opt.upfirdn_variant);
+    int packed = (NCH == 1 && v != 4 && v != 5) ? 1 : 0;
+    if (packed && (v == 0 || v == 7)) packed = 2;
+    if (packed == 2) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs3(taps.c, pairs);
+    else if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
     if constexpr (NCH == 1) {
+        constexpr int WS_LEN = KCP + ((Z > 0) ? 4 : 0) + kPolyNT * SIN + 4;
+        const int stages = (ctx->opt.upfirdn_ws_stages == 2) ? 2 : 3;      // 3 stages, 2 CTAs/SM (default) | 2 stages, 3 CTAs/SM
+        const size_t ws_bytes = (static_cast<size_t>(stages) * WS_LEN + static_cast<size_t>(kPolyNT) * R) * sizeof(float);
+        if (v == 0 && ws_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
+            auto kern = (stages == 2) ? upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 2> : upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 3>;
+            static thread_local size_t configured[16][2] = {};
+            static thread_local int resident[16][2] = {};
+            const int si = stages - 2;
+            if (configured[d][si] < ws_bytes) {
+                SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws_bytes)),
+                          "cudaFuncSetAttribute(upfirdn_ws_kernel)");
+                configured[d][si] = ws_bytes;
+                int nb = 0;
+                SCIR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kWsThreads, ws_bytes),
+                          "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+                resident[d][si] = std::max(nb, 1);
+            }
+            const long long g = std::min<long long>(grid, static_cast<long long>(ctx->sm_count) * resident[d][si]);
+            kern<<<static_cast<unsigned>(g), kWsThreads, ws_bytes, ctx->stream>>>(q, taps, batch, *pairs);
+            SCIR_CUDA(cudaGetLastError(), "upfirdn_ws_kernel launch");
+            ctx->launches++;
+            ctx->poly_launches++;
+            return SCIR_B200_OK;
+        }
         if (ctx->opt.upfirdn_variant == 6) {               // warp-pipelined A/B arm
             constexpr int LEN = KCP + ((Z > 0) ? 4 : 0) + 32 * SIN + 4, WT_OUT = 32 * R;
             const size_t bytes = static_cast<size_t>(kPolyWarps) * (2 * LEN + WT_OUT) * sizeof(float);

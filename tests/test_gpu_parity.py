@@ -369,17 +369,24 @@ def test_upfirdn_tile_kernel_rates(up, down, lead, trail, len_h):
         assert np.abs(yv.cpu().numpy() - want).max() <= tol(h, x)
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5, 6])
-@pytest.mark.parametrize("up,down,len_h", [(3, 2, 97), (2, 3, 61), (1, 2, 33), (4, 3, 40)])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7, 8, 0, 20])
+@pytest.mark.parametrize("up,down,len_h", [(3, 2, 97), (2, 3, 61), (1, 2, 33), (4, 3, 40), (1, 4, 120), (3, 1, 90), (2, 1, 64)])
 def test_upfirdn_kernel_variants_agree(variant, up, down, len_h):
-    """upfirdn_variant: 3 one tile per CTA (FFMA2), 4 streaming scalar FFMA, 5 tile scalar, 6 warp-pipelined (FFMA2):
-    A/B arms of the default streaming FFMA2 kernel; same results to rounding, all inside the oracle tolerance."""
+    """upfirdn_variant: 0 warp-specialised + tap-reuse FFMA2 core (default; 20 = the same with 2 input stages),
+    7 streaming + tap-reuse core, 8 streaming + one tap-pair load per FFMA2 (round-1 default), 3 one tile per CTA (FFMA2),
+    4 streaming scalar FFMA, 5 tile scalar, 6 per-warp pipelines: same results to rounding, all inside the oracle
+    tolerance, on aligned and unaligned views, many more tiles than resident CTAs (every stage and barrier phase cycles)."""
+    if variant == 20:
+        variant, stages = 0, 2
+    else:
+        stages = 3
     rng = np.random.RandomState(variant * 10 + up)
     h = rng.randn(len_h).astype(np.float32)
     x = (rng.rand(5, 70001).astype(np.float32) * 2 - 1)
     want = O.upfirdn(h, x, up, down)
     ctx = gpu.Context(0)
     ctx.set_option("upfirdn_variant", variant)
+    ctx.set_option("upfirdn_ws_stages", stages)
     for view in (dev(x), dev(x)[:, 1:], dev(x)[::2, 3:60000]):
         y = signal.upfirdn(h, view, up, down, ctx=ctx)
         ctx.sync()
@@ -387,6 +394,13 @@ def test_upfirdn_kernel_variants_agree(variant, up, down, len_h):
         assert y.shape == w.shape
         assert np.abs(y.cpu().numpy() - w).max() <= tol(h, x)
     assert want.shape[0] == 5
+    # a launch with far more tiles than resident CTAs, and an extension mode (edge tiles synthesised by the producer)
+    big = (np.random.RandomState(up + down).rand(64, 400003).astype(np.float32) * 2 - 1)
+    yb = signal.upfirdn(h, dev(big), up, down, mode="symmetric", ctx=ctx)
+    ctx.sync()
+    rows = [0, 31, 63]
+    wb = O.upfirdn_mode(h, big[rows], up, down, "symmetric")
+    assert np.abs(yb[rows].cpu().numpy() - wb).max() <= tol(h, big)
 
 
 @pytest.mark.parametrize("up,down,len_h,n", [(160, 147, 3201, 30000), (147, 160, 3201, 30011), (5, 4, 101, 50000), (7, 3, 141, 20000),
