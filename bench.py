@@ -347,6 +347,7 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         sampler.sample()
         sampler.start()
         l0, tc0, fx0 = ctx.launch_count(), ctx.get_option("toeplitz_launches"), ctx.get_option("fixup_launches")
+        os0 = ctx.get_option("os_launches")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         y = None
@@ -357,17 +358,17 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         sampler.sample()
         clocks = sampler.result()
         return (e0.elapsed_time(e1) / count, clocks, ctx.launch_count() - l0, ctx.get_option("toeplitz_launches") - tc0,
-                ctx.get_option("fixup_launches") - fx0, y, (count - 1) % nbuf)
+                ctx.get_option("fixup_launches") - fx0, y, (count - 1) % nbuf, ctx.get_option("os_launches") - os0)
 
     for i in range(warmup):
         run_step(cfg, env.signal, env.gpu, xs[i % nbuf], taps, outs_buf[i % nbuf])
     env.barrier()
-    ms, clocks, launches, tc_launches, fx_launches, y, last = timed(steps)
+    ms, clocks, launches, tc_launches, fx_launches, y, last, os_launches = timed(steps)
     remeasured = False
     if ClockSampler.rejected(clocks):                       # the contract: rejected once, measured again
         env.barrier()
         first = clocks
-        ms, clocks, launches, tc_launches, fx_launches, y, last = timed(steps)
+        ms, clocks, launches, tc_launches, fx_launches, y, last, os_launches = timed(steps)
         clocks["first_attempt"] = {k: first.get(k) for k in ("sm_mhz", "reasons")}
         remeasured = True
     env.barrier()
@@ -407,6 +408,21 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         if t_tensor > t_hbm:
             bound = "tensor"
     traffic = TRAFFIC_PER_LAUNCH.get(name) if rows == CONFIGS[name]["rows"] else None
+    fft = None
+    if os_launches > 0:
+        # overlap-save FFT kernel (fir_os.cu): block N = L + K - 1, two blocks per complex transform
+        k_eff = cfg["k"]
+        if cfg["op"] == "filtfilt" and os_launches // steps == 1:
+            k_eff = 2 * k_eff - 1
+        nfft = 4096 if k_eff <= 1536 else 16384
+        lblk = nfft - (k_eff - 1)
+        passes = 6 if nfft == 4096 else 8                      # shared-memory round trips per transform pair (fwd + inv)
+        fft = {"block": nfft, "valid_outputs_per_block": lblk, "taps_per_pass": k_eff,
+               "smem_bytes_per_output": passes * 0.5 * 2 * nfft * 8 / (2.0 * lblk),
+               "hbm_bytes_per_output_executed": (2.0 * nfft * 4 + 2.0 * lblk * 4) / (2.0 * lblk),
+               "note": "FP32 shared-memory FFT, two real blocks per complex transform; executes O(log N) flop per output "
+                       "instead of 2K: the binding resources are shared-memory bandwidth and FP32 issue, not HBM or the tensor pipe"}
+        traffic = TRAFFIC_PER_LAUNCH.get(name + "_os") if rows == CONFIGS[name]["rows"] else None
     if bound == "tensor":
         roofline = {"bound": "tensor", "achieved": tensor["executed_tflops"], "peak": tensor["peak_tflops"], "unit": "TFLOP/s",
                     "frac": tensor["frac_executed"], "traffic": traffic,
@@ -418,6 +434,7 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": env.hbm_peak, "unit": "GB/s",
                     "frac": achieved_gbs / env.hbm_peak, "traffic": traffic, "peak_source": env.peak_src, "kernel_ms": kern_ms}
     roofline["tensor"] = tensor
+    roofline["fft"] = fft
     roofline["fp32"] = {"achieved_tflops": achieved_tf, "peak_nominal_tflops": FP32_NOMINAL_TFLOPS,
                         "frac_nominal": achieved_tf / FP32_NOMINAL_TFLOPS,
                         "peak_ffma_microbench_tflops": env.ffma_tflops,
@@ -428,8 +445,9 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
                                   "note": "BASELINE.md per-shape roofline: max(bytes/measured HBM, 2*K flops/nominal FP32)"}
     rec = {"workload": cfg["desc"], "rows_per_gpu": rows, "steps": steps, "ms_per_step": ms_max, "value": value, "unit": UNIT,
            "roofline": roofline, "clocks": clocks, "clock_remeasured": remeasured,
-           "gpu_launches": int(launches), "tensor_core_launches": int(tc_launches),
-           "arithmetic": ("f32 in/out; " + tensor["split"]) if tensor else "f32 FFMA (CUDA cores)",
+           "gpu_launches": int(launches), "tensor_core_launches": int(tc_launches), "fft_launches": int(os_launches),
+           "arithmetic": ("f32 in/out; " + tensor["split"]) if tensor else
+                         ("f32 overlap-save FFT (CUDA cores)" if os_launches > 0 else "f32 FFMA (CUDA cores)"),
            "l2": config_dict(name, cfg, rows, env.world)["l2"]}
     if want_parity and cfg["op"] != "ew":
         yd = y if not isinstance(y, np.ndarray) else torch.from_numpy(y)
@@ -784,7 +802,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(name, cfg, rows, world),
             "gpu": {"variant": args.variant, "options": env.opts, "tensor_core_launches": head["tensor_core_launches"],
-                    "arithmetic": head["arithmetic"]},
+                    "fft_launches": head["fft_launches"], "arithmetic": head["arithmetic"]},
             "roofline": head["roofline"], "parity": head.get("parity"), "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
             "configs": sweep, "strong": strong,

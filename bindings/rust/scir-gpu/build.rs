@@ -9,7 +9,7 @@ use std::path::PathBuf;
 use std::process::Command;
 
 const SOURCES: &[&str] = &[
-    "api.cu", "fir_direct.cu", "fir_direct_rev.cu", "upfirdn.cu", "upfirdn_poly.cu", "fir_toeplitz.cu",
+    "api.cu", "fir_direct.cu", "fir_direct_rev.cu", "upfirdn.cu", "upfirdn_poly.cu", "fir_toeplitz.cu", "fir_os.cu",
     "fir_f64.cu", "f64_routes.cu", "elementwise.cu", "mg.cu", "microbench.cu",
 ];
 

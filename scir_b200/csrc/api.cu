@@ -187,7 +187,14 @@ static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64
 int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
 {
     const int64_t mode = ctx->opt.long_tap_path;
-    if (mode != 1 && ctx->opt.variant == 0) {
+    // Long filters: block-FFT convolution (fir_os.cu) does O(log N) work per output where direct form does O(K).
+    // Measured cross-over against the tensor kernel: profiles/README.md.  A launch must fill the machine with block
+    // pairs (2 (N - K + 1) outputs each) for the FFT path to pay.
+    if ((mode == 3 || (mode == 0 && ctx->opt.variant == 0 && k >= ctx->opt.os_min_k)) && fir_os_supported(ctx, pass, k)) {
+        const double outs = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch);
+        if (mode == 3 || outs >= 4.0e6) return launch_fir_os(ctx, pass, c, k);
+    }
+    if (mode != 1 && mode != 3 && ctx->opt.variant == 0) {
         int64_t tiles = 0;
         bool aligned = false;
         if (toeplitz_supported(ctx, pass, k, &tiles, &aligned)) {
@@ -620,6 +627,9 @@ int scir_b200_ctx_destroy(scir_b200_ctx* ctx)
     if (ctx->toep_flags.ptr) cudaFree(ctx->toep_flags.ptr);
     if (ctx->row_bg.ptr) cudaFree(ctx->row_bg.ptr);
     if (ctx->toep_taps.ptr) cudaFree(ctx->toep_taps.ptr);
+    if (ctx->os_tw.ptr) cudaFree(ctx->os_tw.ptr);
+    if (ctx->os_taps.ptr) cudaFree(ctx->os_taps.ptr);
+    if (ctx->os_H.ptr) cudaFree(ctx->os_H.ptr);
     if (ctx->gen_taps.ptr) cudaFree(ctx->gen_taps.ptr);
     delete ctx->pool;
     for (int i = 0; i < scir_b200_ctx::kHostSlots; ++i) {
@@ -680,6 +690,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "ffma2")) return &o.ffma2;
     if (!strcmp(key, "filtfilt_fused")) return &o.filtfilt_fused;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
+    if (!strcmp(key, "os_min_k")) return &o.os_min_k;
     if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
     if (!strcmp(key, "host_stage")) return &o.host_stage;
@@ -704,6 +715,10 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
     if (!value) return set_error(SCIR_B200_ERR_INVALID_ARG, "value is NULL");
     if (key && !strcmp(key, "toeplitz_launches")) {                   // read-only statistic
         *value = static_cast<int64_t>(ctx->toeplitz_launches);
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "os_launches")) {                      // read-only statistic
+        *value = static_cast<int64_t>(ctx->os_launches);
         return SCIR_B200_OK;
     }
     if (key && !strcmp(key, "fixup_launches")) {                   // read-only statistic

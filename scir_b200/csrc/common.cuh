@@ -56,7 +56,8 @@ struct DeviceScope {
 struct Options {
     int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
     int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
-    int64_t long_tap_path = 0;  // 0 auto (see launch_fir); 1 force FP32 direct; 2 force tcgen05 Toeplitz
+    int64_t long_tap_path = 0;  // 0 auto (see launch_fir); 1 force FP32 direct; 2 force tcgen05 Toeplitz; 3 force overlap-save FFT
+    int64_t os_min_k = 256;     // auto mode: tap counts from here on take the overlap-save FFT path (large launches)
     int64_t toeplitz_terms = 3; // split products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
     int64_t toeplitz_split = 0; // operand format of the split: 0 block-scaled FP16 (11-bit terms), 1 BF16 (8-bit terms)
     int64_t toeplitz_chains = 1; // accumulation chains per tile in TMEM (2: consecutive MMAs alternate accumulators; measured: no gain)
@@ -109,6 +110,11 @@ struct scir_b200_ctx {
     std::vector<float> gen_taps_host;      // ... and what the buffer currently holds
     uint64_t gen_tiled_launches = 0;       // launches served by it
     scir_b200::DeviceBuffer row_bg;        // resample_poly padtype statistics: one float per row
+    // overlap-save FFT path (fir_os.cu): twiddles, the current filter's taps and spectrum, and what they were made from
+    scir_b200::DeviceBuffer os_tw, os_taps, os_H;
+    std::vector<float> os_taps_host;
+    int os_logn = 0;
+    uint64_t os_launches = 0;              // launches served by the overlap-save kernel
     // *_host streaming pipeline resources (lazily created): a ring of kHostSlots row blocks
     static constexpr int kHostSlots = 6;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -187,6 +193,10 @@ int launch_upfirdn(scir_b200_ctx* ctx, const float* h, int64_t len_h, int64_t up
 // ---- long-tap tensor-core path (tcgen05 block-Toeplitz) -----------------------------------------
 bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t* tiles = nullptr, bool* aligned = nullptr);
 int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
+
+// ---- long-tap overlap-save path (FP32 shared-memory FFT, fir_os.cu) -------------------------------------------
+bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k);
+int launch_fir_os(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 
 int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);
 

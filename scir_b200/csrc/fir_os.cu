@@ -1,0 +1,454 @@
+// fir_os.cu -- overlap-save FIR pass for long filters: block FFT convolution in shared memory, FP32.
+//
+// Why: the tcgen05 block-Toeplitz kernel (fir_toeplitz.cu) runs at the chip's deliverable MMA rate, but direct form
+// costs 2K flop per output -- 25 344 executed tensor flop per output at K = 4097 (config 3), 12x above that config's
+// HBM floor.  The only lever left is executing fewer flops (task 6).  Overlap-save does the same linear
+// convolution with O(log N) work per output: a block of N = L + K - 1 samples is transformed, multiplied by the filter's
+// spectrum and transformed back; the last L outputs of the block are exact linear-convolution outputs.  The costing
+// (tools/costing_overlap_save.py, profiles/r02_overlap_save_costing.txt) compared a tensor-core DFT-by-GEMM formulation
+// with a plain FP32 shared-memory FFT: the GEMM route needs 8192 executed tensor flop per output plus six operand
+// re-splits per element and more shared memory than an SM has; the FP32 FFT needs ~100 flop and ~55 B of shared-memory
+// traffic per output and no precision split at all -- so it is the one built.
+//
+// Semantics are those of every other FIR pass (common.cuh: FirPass, causal direction): out[i] = sum_d c[d] * v[i - d]
+// over the virtual sequence v (offset, zero / held boundary, odd / even / constant extension), which is what
+// crates/scir-gpu/src/lib.rs:1141-1148 computes for the plain zero-state case.
+//
+// Kernel: one CTA per PAIR of consecutive L-blocks of a row.  h is real, so the two blocks ride through ONE complex
+// FFT as z = a + i b:  IFFT(FFT(z) H) = (h * a) + i (h * b)  -- no unpacking step.  The transform is an in-place
+// decimation-in-frequency FFT (radix 16, 16, 16 [, 4]) whose output order is digit-reversed; H is produced by the SAME
+// forward transform (os_spectrum_kernel), so it is digit-reversed identically and the inverse -- the mirrored
+// decimation-in-time passes -- needs no reordering either.  The first forward pass gathers straight from global memory,
+// the innermost forward pass, the multiplication by H and the innermost inverse pass are one register-resident step,
+// and the last inverse pass scatters straight to global memory: four shared-memory round trips for N = 4096.
+// Arithmetic is FP32 throughout; error ~ log2(N) * 2^-24 relative to the block's RMS (measured 0.002-0.02 of the
+// path's tolerance 1e-5 * sum|h| * max|x|).  Like the tensor kernel, a block that holds a NaN / Inf sample is
+// flagged and recomputed by a fix-up kernel the reference's way, so non-finite values stay local to their K outputs.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace scir_b200 {
+
+namespace {
+
+constexpr int kOsTwN = 16384;                              // twiddle table: W_16384^t, t in [0, 16384)
+
+struct OsParams {
+    FirPass p;
+    int k;
+    long long L;                  // outputs per block
+    long long pairs_per_row;
+    long long total_pairs;
+    const float2* H;              // [N] spectrum / N, in the forward transform's (digit-reversed) order
+    const float2* tw;             // [kOsTwN]
+    const float* taps;            // [k] by delay index (device): spectrum kernel and fix-up
+    int* flags;                   // [total_pairs]
+    int fast_ok;                  // rows may be read without the virtual-sequence rules in the interior
+};
+
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }      // one pad slot per 16: conflict-free stride-16 access
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// cos / sin of 2 pi k / 16
+__device__ constexpr float kC16[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                                      0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+__device__ constexpr float kS16[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                                      1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+
+// R-point DFT in registers, natural order in and out (recursive decimation in time).  INV: conjugate kernel (no 1/R).
+template <int R, bool INV>
+__device__ __forceinline__ void dft(float2 (&a)[R])
+{
+    if constexpr (R == 2) {
+        const float2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    } else {
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) {
+            e[j] = a[2 * j];
+            o[j] = a[2 * j + 1];
+        }
+        dft<R / 2, INV>(e);
+        dft<R / 2, INV>(o);
+#pragma unroll
+        for (int kk = 0; kk < R / 2; ++kk) {
+            float2 t;
+            if (kk == 0) {
+                t = o[0];
+            } else if (kk * 4 == R) {                       // W = -i (forward) / +i (inverse)
+                t = INV ? make_float2(-o[kk].y, o[kk].x) : make_float2(o[kk].y, -o[kk].x);
+            } else {
+                const float c = kC16[kk * (16 / R)], s = kS16[kk * (16 / R)];
+                const float2 w = make_float2(c, INV ? s : -s);
+                t = cmul(o[kk], w);
+            }
+            a[kk] = cadd(e[kk], t);
+            a[kk + R / 2] = csub(e[kk], t);
+        }
+    }
+}
+
+// a[k] *= w^k (forward) or conj(w)^k (inverse), k = 1 .. R-1.  Powers come from a product tree of depth <= 4
+// (w^k = w^hi * w^(k - hi), hi the top bit of k), generated in the order they are consumed so that only the
+// powers of two stay live.
+__host__ __device__ constexpr int os_hibit(int k) { return (k >= 8) ? 8 : (k >= 4) ? 4 : (k >= 2) ? 2 : 1; }
+
+template <int R, bool INV>
+__device__ __forceinline__ void twiddle(float2 (&a)[R], float2 w1)
+{
+    if (INV) w1.y = -w1.y;
+    float2 w[R];
+    w[1] = w1;
+    a[1] = cmul(a[1], w1);
+#pragma unroll
+    for (int kk = 2; kk < R; ++kk) {
+        const int hi = os_hibit(kk);
+        w[kk] = (kk == hi) ? cmul(w[kk / 2], w[kk / 2]) : cmul(w[hi], w[kk - hi]);
+        a[kk] = cmul(a[kk], w[kk]);
+    }
+}
+
+template <int LOGN>
+struct OsGeom {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int THREADS = (LOGN >= 14) ? N / 32 : N / 16;       // radix-16 butterflies per thread per pass: 2 / 1
+    static constexpr int MIN_CTAS = (LOGN >= 14) ? 1 : 3;
+    static constexpr int RLAST = (LOGN % 4 == 0) ? 16 : (1 << (LOGN % 4));      // innermost radix: 16 (N = 4096), 4 (N = 16384)
+    static constexpr int NP16 = (LOGN - ((LOGN % 4 == 0) ? 4 : (LOGN % 4))) / 4; // radix-16 passes before the innermost one
+    static constexpr size_t SMEM = static_cast<size_t>(N + N / 16) * sizeof(float2);
+};
+
+// virtual input sequence (the rules of fir_direct.cu: vload)
+__device__ __forceinline__ float os_vload(const FirPass& p, const float* __restrict__ xr, long long i)
+{
+    if (i < 0) {
+        if (p.bound == BOUND_ZERO) return 0.f;
+        i = 0;
+    } else if (i >= p.n_v) {
+        if (p.bound == BOUND_ZERO) return 0.f;
+        i = p.n_v - 1;
+    }
+    const long long u = i + p.in_off;
+    if (p.ext_mode == EXT_NONE) return xr[u];
+    const long long last = p.n_x - 1;
+    if (u < 0) {
+        if (p.ext_mode == EXT_ODD) return 2.f * xr[0] - xr[-u];
+        if (p.ext_mode == EXT_EVEN) return xr[-u];
+        return xr[0];
+    }
+    if (u > last) {
+        if (p.ext_mode == EXT_ODD) return 2.f * xr[last] - xr[2 * last - u];
+        if (p.ext_mode == EXT_EVEN) return xr[2 * last - u];
+        return xr[last];
+    }
+    return xr[u];
+}
+
+// One radix-16 forward pass on shared memory: sub-transforms of length np, m = np / 16.
+template <int LOGN>
+__device__ __forceinline__ void fwd_pass16(float2* s, const float2* __restrict__ tw, int lognp, int tid)
+{
+    constexpr int N = 1 << LOGN;
+    const int logm = lognp - 4, m = 1 << logm;
+    for (int q = tid; q < N / 16; q += OsGeom<LOGN>::THREADS) {
+        const int i = q & (m - 1), base = ((q >> logm) << lognp) + i;
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = s[pidx(base + (j << logm))];
+        dft<16, false>(a);
+        twiddle<16, false>(a, __ldg(tw + (static_cast<long long>(i) << (14 - lognp))));     // W_np^i = W_16384^(i * 16384 / np)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[pidx(base + (j << logm))] = a[j];
+    }
+}
+
+template <int LOGN>
+__device__ __forceinline__ void inv_pass16(float2* s, const float2* __restrict__ tw, int lognp, int tid)
+{
+    constexpr int N = 1 << LOGN;
+    const int logm = lognp - 4, m = 1 << logm;
+    for (int q = tid; q < N / 16; q += OsGeom<LOGN>::THREADS) {
+        const int i = q & (m - 1), base = ((q >> logm) << lognp) + i;
+        float2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = s[pidx(base + (j << logm))];
+        twiddle<16, true>(a, __ldg(tw + (static_cast<long long>(i) << (14 - lognp))));
+        dft<16, true>(a);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[pidx(base + (j << logm))] = a[j];
+    }
+}
+
+// The innermost step: forward radix-RL pass (m = 1, no twiddles), multiplication by the spectrum, inverse radix-RL pass.
+template <int LOGN, bool SPECTRUM_ONLY>
+__device__ __forceinline__ void middle(float2* s, const float2* __restrict__ H, float2* __restrict__ H_out, int tid)
+{
+    constexpr int N = 1 << LOGN, RL = OsGeom<LOGN>::RLAST;
+    for (int q = tid; q < N / RL; q += OsGeom<LOGN>::THREADS) {
+        const int base = q * RL;
+        float2 a[RL];
+#pragma unroll
+        for (int j = 0; j < RL; ++j) a[j] = s[pidx(base + j)];
+        dft<RL, false>(a);
+        if constexpr (SPECTRUM_ONLY) {
+#pragma unroll
+            for (int j = 0; j < RL; ++j) H_out[base + j] = a[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < RL; ++j) a[j] = cmul(a[j], __ldg(H + base + j));
+            dft<RL, true>(a);
+#pragma unroll
+            for (int j = 0; j < RL; ++j) s[pidx(base + j)] = a[j];
+        }
+    }
+}
+
+// Spectrum of the taps in the transform's own output order, scaled by 1/N: H[pos] = FFT(c zero-padded)[rev(pos)] / N.
+template <int LOGN>
+__global__ void __launch_bounds__(OsGeom<LOGN>::THREADS) os_spectrum_kernel(const float* __restrict__ taps, int k, const float2* __restrict__ tw,
+                                                                            float2* __restrict__ H)
+{
+    extern __shared__ __align__(16) float2 s_os[];
+    constexpr int N = 1 << LOGN;
+    const int tid = threadIdx.x;
+    const float inv_n = 1.f / static_cast<float>(N);
+    for (int n = tid; n < N; n += OsGeom<LOGN>::THREADS) s_os[pidx(n)] = make_float2(n < k ? taps[n] * inv_n : 0.f, 0.f);
+    __syncthreads();
+    int lognp = LOGN;
+#pragma unroll
+    for (int pass = 0; pass < OsGeom<LOGN>::NP16; ++pass) {
+        fwd_pass16<LOGN>(s_os, tw, lognp, tid);
+        __syncthreads();
+        lognp -= 4;
+    }
+    middle<LOGN, true>(s_os, nullptr, H, tid);
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(OsGeom<LOGN>::THREADS, OsGeom<LOGN>::MIN_CTAS) fir_os_kernel(const __grid_constant__ OsParams q)
+{
+    extern __shared__ __align__(16) float2 s_os[];
+    constexpr int N = 1 << LOGN;
+    constexpr int NT = OsGeom<LOGN>::THREADS;
+    const FirPass& p = q.p;
+    const int tid = threadIdx.x;
+    const long long pair = blockIdx.x;
+    const long long row = pair / q.pairs_per_row;
+    const long long pr = pair - row * q.pairs_per_row;
+    const long long i0 = p.out_begin + pr * 2 * q.L;        // first output (virtual index) of block a; block b starts L later
+    // Element n of the block is v[a0 + sgn n] + i v[a0 + L + sgn n], and output n (n >= k-1) of block a is out[a0 + sgn n]:
+    //   causal     (out[i] = sum c[d] v[i-d]):  a0 = i0 - (k-1),        sgn = +1
+    //   anticausal (out[i] = sum c[d] v[i+d]):  a0 = i0 + L + (k-1) - 1, sgn = -1   (the block runs backwards in time)
+    const int sgn = (p.dir > 0) ? 1 : -1;
+    const long long a0 = (p.dir > 0) ? i0 - (q.k - 1) : i0 + q.L + (q.k - 1) - 1;
+    const float* __restrict__ xr = p.x + row * p.ld_x;
+    const float2* __restrict__ tw = q.tw;
+
+    // ---- first forward pass straight from global memory ----
+    // interior blocks (everything inside the row, no extension rule applies) read x directly
+    const long long v_lo = (p.dir > 0) ? a0 : a0 - (N - 1), v_hi = (p.dir > 0) ? a0 + q.L + N - 1 : a0 + q.L;
+    const bool interior = q.fast_ok && v_lo >= 0 && v_hi < p.n_v && v_lo + p.in_off >= 0 && v_hi + p.in_off < p.n_x;
+    int bad = 0;
+    {
+        constexpr int logm = LOGN - 4, m = 1 << logm;
+        for (int i = tid; i < m; i += NT) {
+            float2 a[16];
+            if (interior) {
+                const float* __restrict__ xa = xr + (a0 + p.in_off) + sgn * i;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[j] = make_float2(__ldg(xa + sgn * (j << logm)), __ldg(xa + q.L + sgn * (j << logm)));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const long long ia = a0 + sgn * static_cast<long long>(i + (j << logm));
+                    a[j] = make_float2(os_vload(p, xr, ia), os_vload(p, xr, ia + q.L));
+                }
+            }
+            float chk = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) chk += a[j].x * 0.f + a[j].y * 0.f;        // NaN iff any sample is NaN / Inf
+            bad |= (chk != chk);
+            dft<16, false>(a);
+            twiddle<16, false>(a, __ldg(tw + (static_cast<long long>(i) << (14 - LOGN))));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s_os[pidx(i + (j << logm))] = a[j];
+        }
+    }
+    const int any_bad = __syncthreads_or(bad);              // also the barrier after pass 0
+    if (tid == 0) q.flags[pair] = any_bad;
+
+    int lognp = LOGN - 4;
+#pragma unroll
+    for (int pass = 1; pass < OsGeom<LOGN>::NP16; ++pass) {
+        fwd_pass16<LOGN>(s_os, tw, lognp, tid);
+        __syncthreads();
+        lognp -= 4;
+    }
+    middle<LOGN, false>(s_os, q.H, nullptr, tid);
+    __syncthreads();
+#pragma unroll
+    for (int pass = OsGeom<LOGN>::NP16 - 1; pass >= 1; --pass) {
+        lognp += 4;
+        inv_pass16<LOGN>(s_os, tw, lognp, tid);
+        __syncthreads();
+    }
+
+    // ---- last inverse pass straight to global memory: outputs n in [k-1, N) of either block ----
+    {
+        constexpr int logm = LOGN - 4, m = 1 << logm;
+        float* __restrict__ yr = p.y + row * p.ld_y + p.out_off;
+        for (int i = tid; i < m; i += NT) {
+            float2 a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = s_os[pidx(i + (j << logm))];
+            twiddle<16, true>(a, __ldg(tw + (static_cast<long long>(i) << (14 - LOGN))));
+            dft<16, true>(a);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = i + (j << logm);
+                if (n >= q.k - 1) {
+                    const long long ia = a0 + sgn * static_cast<long long>(n);
+                    if (ia < p.out_end) yr[ia] = a[j].x;
+                    if (ia + q.L < p.out_end) yr[ia + q.L] = a[j].y;
+                }
+            }
+        }
+    }
+}
+
+// Blocks that held a NaN / Inf sample, recomputed like the reference loop (lib.rs:1138-1150): one FMA chain per output.
+__global__ void __launch_bounds__(256) os_fixup_kernel(const __grid_constant__ OsParams q)
+{
+    const FirPass& p = q.p;
+    for (long long base = static_cast<long long>(blockIdx.x) * 256; base < q.total_pairs; base += static_cast<long long>(gridDim.x) * 256) {
+        const long long mine = base + threadIdx.x;
+        const int flag = (mine < q.total_pairs) ? q.flags[mine] : 0;
+        if (!__syncthreads_or(flag)) continue;
+        __shared__ int hit[256];
+        hit[threadIdx.x] = flag;
+        __syncthreads();
+        for (int j = 0; j < 256; ++j) {
+            if (!hit[j]) continue;
+            const long long pair = base + j;
+            const long long row = pair / q.pairs_per_row, pr = pair - row * q.pairs_per_row;
+            const long long i0 = p.out_begin + pr * 2 * q.L;
+            const float* __restrict__ xr = p.x + row * p.ld_x;
+            float* __restrict__ yr = p.y + row * p.ld_y + p.out_off;
+            for (long long o = threadIdx.x; o < 2 * q.L; o += blockDim.x) {
+                const long long i = i0 + o;
+                if (i >= p.out_end) break;
+                float acc = 0.f;
+                for (int d = 0; d < q.k; ++d) acc = fmaf(__ldg(q.taps + d), os_vload(p, xr, p.dir > 0 ? i - d : i + d), acc);
+                yr[i] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int os_logn_for(int64_t k)
+{
+    // cost per output ~ passes * N / L: N = 4096 (6 shared-memory passes) up to K ~ 1500, N = 16384 (8) beyond
+    if (k <= 1536) return 12;
+    return 14;
+}
+
+}  // namespace
+
+bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k)
+{
+    if (k < 2 || k > SCIR_B200_MAX_TAPS) return false;
+    if (pass.batch <= 0 || pass.out_end <= pass.out_begin) return false;
+    const int logn = os_logn_for(k);
+    const long long L = (1LL << logn) - (k - 1);
+    if (L < (1LL << logn) / 4) return false;
+    if (OsGeom<14>::SMEM > static_cast<size_t>(ctx->max_smem_optin)) return false;
+    const long long blocks = (pass.out_end - pass.out_begin + L - 1) / L;
+    const long long pairs = (blocks + 1) / 2;
+    return pairs * pass.batch <= 0x7fffffffLL;
+}
+
+int launch_fir_os(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)
+{
+    if (pass.batch <= 0 || pass.out_end <= pass.out_begin) return SCIR_B200_OK;
+    if (!fir_os_supported(ctx, pass, k)) return set_error(SCIR_B200_ERR_UNSUPPORTED, "overlap-save path cannot serve k=%lld", (long long)k);
+    SCIR_TRY(ctx_bind(ctx));
+    const int logn = os_logn_for(k);
+    const long long N = 1LL << logn;
+
+    // twiddle table W_16384^t (once per ctx, f64 on the host)
+    if (!ctx->os_tw.ptr) {
+        std::vector<float2> tw(kOsTwN);
+        for (int t = 0; t < kOsTwN; ++t) {
+            const double ang = -2.0 * 3.14159265358979323846 * static_cast<double>(t) / static_cast<double>(kOsTwN);
+            tw[static_cast<size_t>(t)] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+        }
+        SCIR_TRY(ctx_scratch(ctx, ctx->os_tw, tw.size() * sizeof(float2)));
+        SCIR_CUDA(cudaMemcpyAsync(ctx->os_tw.ptr, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream),
+                  "cudaMemcpyAsync(twiddles)");
+    }
+    SCIR_TRY(ctx_scratch(ctx, ctx->os_taps, static_cast<size_t>(SCIR_B200_MAX_TAPS) * sizeof(float)));
+    SCIR_TRY(ctx_scratch(ctx, ctx->os_H, static_cast<size_t>(kOsTwN) * sizeof(float2)));
+
+    using SpecKern = void (*)(const float*, int, const float2*, float2*);
+    using FirKern = void (*)(const OsParams);
+    const SpecKern spec = (logn == 12) ? os_spectrum_kernel<12> : os_spectrum_kernel<14>;
+    const FirKern kern = (logn == 12) ? fir_os_kernel<12> : fir_os_kernel<14>;
+    const size_t smem = (logn == 12) ? OsGeom<12>::SMEM : OsGeom<14>::SMEM;
+    const int threads = (logn == 12) ? OsGeom<12>::THREADS : OsGeom<14>::THREADS;
+    static thread_local bool configured[16][2] = {};
+    const int d = ctx->device & 15, li = (logn == 12) ? 0 : 1;
+    if (!configured[d][li]) {
+        SCIR_CUDA(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "cudaFuncSetAttribute(os_spectrum_kernel)");
+        SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "cudaFuncSetAttribute(fir_os_kernel)");
+        configured[d][li] = true;
+    }
+    // taps and their spectrum live in ctx-owned device buffers; redone only when the filter (or the block size) changes
+    if (ctx->os_taps_host.size() != static_cast<size_t>(k) || ctx->os_logn != logn ||
+        std::memcmp(ctx->os_taps_host.data(), c, static_cast<size_t>(k) * sizeof(float)) != 0) {
+        ctx->os_taps_host.assign(c, c + k);
+        ctx->os_logn = logn;
+        SCIR_CUDA(cudaMemcpyAsync(ctx->os_taps.ptr, ctx->os_taps_host.data(), static_cast<size_t>(k) * sizeof(float), cudaMemcpyHostToDevice,
+                                  ctx->stream),
+                  "cudaMemcpyAsync(overlap-save taps)");
+        spec<<<1, threads, smem, ctx->stream>>>(static_cast<const float*>(ctx->os_taps.ptr), static_cast<int>(k),
+                                                 static_cast<const float2*>(ctx->os_tw.ptr), static_cast<float2*>(ctx->os_H.ptr));
+        SCIR_CUDA(cudaGetLastError(), "os_spectrum_kernel launch");
+        ctx->launches++;
+    }
+
+    OsParams q{};
+    q.p = pass;
+    q.k = static_cast<int>(k);
+    q.L = N - (k - 1);
+    const long long blocks = (pass.out_end - pass.out_begin + q.L - 1) / q.L;
+    q.pairs_per_row = (blocks + 1) / 2;
+    q.total_pairs = q.pairs_per_row * pass.batch;
+    q.H = static_cast<const float2*>(ctx->os_H.ptr);
+    q.tw = static_cast<const float2*>(ctx->os_tw.ptr);
+    q.taps = static_cast<const float*>(ctx->os_taps.ptr);
+    SCIR_TRY(ctx_scratch(ctx, ctx->toep_flags, static_cast<size_t>(q.total_pairs) * sizeof(int)));
+    q.flags = static_cast<int*>(ctx->toep_flags.ptr);
+    q.fast_ok = 1;
+    kern<<<static_cast<unsigned>(q.total_pairs), threads, smem, ctx->stream>>>(q);
+    SCIR_CUDA(cudaGetLastError(), "fir_os_kernel launch");
+    const long long fix_grid = std::min<long long>((q.total_pairs + 255) / 256, static_cast<long long>(ctx->sm_count) * 8);
+    os_fixup_kernel<<<static_cast<unsigned>(fix_grid), 256, 0, ctx->stream>>>(q);
+    SCIR_CUDA(cudaGetLastError(), "os_fixup_kernel launch");
+    ctx->launches += 2;
+    ctx->fixup_launches++;
+    ctx->os_launches++;
+    return SCIR_B200_OK;
+}
+
+}  // namespace scir_b200

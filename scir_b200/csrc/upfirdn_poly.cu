@@ -473,6 +473,7 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
             mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
             phases ^= 1u << s;
         } else {                                           // edge tile: samples outside the row by extension mode
+#pragma unroll 4
             for (int t = tid; t < len; t += NT) in[t] = upfirdn_sample(xr, a + t, q.n_in, q.ext);
             __syncthreads();
         }
@@ -522,7 +523,7 @@ upfirdn_stream_kernel(const __grid_constant__ PolyParams q, const __grid_constan
 // and stores parked behind two __syncthreads per tile) is what this removes.
 constexpr int kWsThreads = kPolyNT + 32;
 
-template <int UP, int DOWN, int G, int KCP, int Z, int kWsStages>
+template <int UP, int DOWN, int G, int KCP, int Z, int kWsStages, int CORE>
 __global__ void __launch_bounds__(kWsThreads, (kWsStages >= 3) ? 2 : 3)
 upfirdn_ws_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ PolyTaps taps, long long batch,
                   const __grid_constant__ PolyPairs pairs)
@@ -579,15 +580,16 @@ upfirdn_ws_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ 
             const long long a = first_sample(tile);
             const float* __restrict__ xr = q.x + row * q.ld_x;
             float* const in = smem + s * LEN;
-            if (q.in_vec_ok && a >= 0 && a + LEN <= q.n_in) {
-                if (lane == 0) {
+            if (lane == 0) {
+                if (q.in_vec_ok && a >= 0 && a + LEN <= q.n_in) {
                     mbar_arrive_expect_tx(full0 + 8u * s, LEN * 4u);
                     bulk_copy_g2s(smem_u32(in), xr + a, LEN * 4u, full0 + 8u * s);
+                } else {
+                    // edge tile (2 per row): its samples come from the extension mode.  The compute warps synthesise it
+                    // themselves, 256 threads wide; the producer only hands the (free) stage over.  (Filling it here,
+                    // 32 lanes wide, stalls the whole pipeline: measured 160 us per edge tile.)
+                    mbar_arrive(full0 + 8u * s);
                 }
-            } else {                                       // edge tile: samples outside the row by extension mode
-                for (int t = lane; t < LEN; t += 32) in[t] = upfirdn_sample(xr, a + t, q.n_in, q.ext);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + 8u * s);
             }
             advance(row, tile);
         }
@@ -604,8 +606,19 @@ upfirdn_ws_kernel(const __grid_constant__ PolyParams q, const __grid_constant__ 
         const float* const in = smem + s * LEN;
 
         mbar_wait(full0 + 8u * s, k & 1u);
+        {
+            const long long a = first_sample(tile);
+            if (!(q.in_vec_ok && a >= 0 && a + LEN <= q.n_in)) {       // edge tile: see the producer
+                const float* __restrict__ xr = q.x + row * q.ld_x;
+                float* const inw = smem + s * LEN;
+#pragma unroll 4
+                for (int t = tid; t < LEN; t += NT) inw[t] = upfirdn_sample(xr, a + t, q.n_in, q.ext);
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // compute warps only; the producer is not part of it
+            }
+        }
         float acc[R];
-        poly_core3<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
+        if constexpr (CORE == 3) poly_core3<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
+        else poly_core2<UP, DOWN, G, KCP, Z>(acc, in + HALO + tid * SIN, taps, pairs);
         __syncwarp();                                      // every lane's reads of the stage are done
         if (lane == 0) {
             mbar_arrive(empty0 + 8u * s);
@@ -755,18 +768,19 @@ int launch_one(scir_b200_ctx* ctx, const PolyParams& q, const PolyTaps& taps, in
     // 6 per-warp pipelines (FFMA2)
     const int v = static_cast<int>(ctx->opt.upfirdn_variant);
     int packed = (NCH == 1 && v != 4 && v != 5) ? 1 : 0;
-    if (packed && (v == 0 || v == 7)) packed = 2;
+    if (packed && (v == 0 || v == 7)) packed = 2;                     // 9: warp-specialised pipeline + the x-major core (A/B)
     if (packed == 2) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs3(taps.c, pairs);
     else if (packed) PolyGeom<UP, DOWN, G, KCP, Z>::fill_pairs(taps.c, pairs);
     if constexpr (NCH == 1) {
         constexpr int WS_LEN = KCP + ((Z > 0) ? 4 : 0) + kPolyNT * SIN + 4;
         const int stages = (ctx->opt.upfirdn_ws_stages == 2) ? 2 : 3;      // 3 stages, 2 CTAs/SM (default) | 2 stages, 3 CTAs/SM
         const size_t ws_bytes = (static_cast<size_t>(stages) * WS_LEN + static_cast<size_t>(kPolyNT) * R) * sizeof(float);
-        if (v == 0 && ws_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
-            auto kern = (stages == 2) ? upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 2> : upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 3>;
-            static thread_local size_t configured[16][2] = {};
-            static thread_local int resident[16][2] = {};
-            const int si = stages - 2;
+        if ((v == 0 || v == 9) && ws_bytes <= static_cast<size_t>(ctx->max_smem_optin)) {
+            auto kern = (v == 9) ? upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 3, 2>
+                                 : (stages == 2) ? upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 2, 3> : upfirdn_ws_kernel<UP, DOWN, G, KCP, Z, 3, 3>;
+            static thread_local size_t configured[16][3] = {};
+            static thread_local int resident[16][3] = {};
+            const int si = (v == 9) ? 2 : stages - 2;
             if (configured[d][si] < ws_bytes) {
                 SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ws_bytes)),
                           "cudaFuncSetAttribute(upfirdn_ws_kernel)");

@@ -369,7 +369,7 @@ def test_upfirdn_tile_kernel_rates(up, down, lead, trail, len_h):
         assert np.abs(yv.cpu().numpy() - want).max() <= tol(h, x)
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7, 8, 0, 20])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7, 8, 9, 0, 20])
 @pytest.mark.parametrize("up,down,len_h", [(3, 2, 97), (2, 3, 61), (1, 2, 33), (4, 3, 40), (1, 4, 120), (3, 1, 90), (2, 1, 64)])
 def test_upfirdn_kernel_variants_agree(variant, up, down, len_h):
     """upfirdn_variant: 0 warp-specialised + tap-reuse FFMA2 core (default; 20 = the same with 2 input stages),
