@@ -414,7 +414,7 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         k_eff = cfg["k"]
         if cfg["op"] == "filtfilt" and os_launches // steps == 1:
             k_eff = 2 * k_eff - 1
-        nfft = 4096 if k_eff <= 1536 else 16384
+        nfft = 4096 if k_eff <= 640 else 16384
         lblk = nfft - (k_eff - 1)
         passes = 6 if nfft == 4096 else 8                      # shared-memory round trips per transform pair (fwd + inv)
         fft = {"block": nfft, "valid_outputs_per_block": lblk, "taps_per_pass": k_eff,

@@ -358,8 +358,10 @@ __global__ void __launch_bounds__(256) os_fixup_kernel(const __grid_constant__ O
 
 int os_logn_for(int64_t k)
 {
-    // cost per output ~ passes * N / L: N = 4096 (6 shared-memory passes) up to K ~ 1500, N = 16384 (8) beyond
-    if (k <= 1536) return 12;
+    // cost per output ~ instructions per transform / L.  Measured (profiles/README.md): 4.3 ps per output with N = 4096
+    // blocks at K = 509 (L = 3588) against 5.4 ps with N = 16384 at K = 4097 (L = 12288); scaled by N / L the larger
+    // block wins from K ~ 650 on
+    if (k <= 640) return 12;
     return 14;
 }
 

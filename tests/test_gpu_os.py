@@ -32,7 +32,7 @@ def run(ctx, fn):
 
 
 @pytest.mark.parametrize("batch,n,k", [(1, 16384, 2), (2, 20000, 63), (3, 40000, 255), (2, 33000, 509), (2, 9000, 1025),
-                                       (1, 100000, 1536), (1, 100000, 1537), (2, 70000, 4097), (1, 40000, 7936), (1, 5, 3),
+                                       (1, 100000, 640), (1, 100000, 641), (1, 100000, 1537), (2, 70000, 4097), (1, 40000, 7936), (1, 5, 3),
                                        (2, 127, 200), (5, 16385, 64), (1, 3588, 509), (1, 3589, 509), (1, 7176, 509), (1, 7177, 509)])
 def test_os_fir_vs_oracle(batch, n, k):
     rng = np.random.RandomState(batch * 131 + n + k)
