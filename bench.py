@@ -310,6 +310,15 @@ class Env:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
         return float(t.item())
 
+    def all_ranks(self, v):
+        """[v on rank 0, v on rank 1, ...] (device all-gather of one float64)"""
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        if self.world == 1:
+            return [float(t.item())]
+        out = self.torch.empty(self.world, device=self.dev, dtype=self.torch.float64)
+        self.dist.all_gather_into_tensor(out, t)
+        return [float(x) for x in out.tolist()]
+
     def sum_over_ranks(self, v):
         t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
         if self.world > 1:
@@ -342,6 +351,8 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
     for key, val in env.opts.items():
         ctx.set_option(key, val)
 
+    step_stats = {}
+
     def timed(count):
         sampler = ClockSampler(env.local_rank)
         sampler.sample()
@@ -349,14 +360,22 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         l0, tc0, fx0 = ctx.launch_count(), ctx.get_option("toeplitz_launches"), ctx.get_option("fixup_launches")
         os0 = ctx.get_option("os_launches")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(min(count, 64))]      # per-step spread (diagnostic)
         e0.record()
         y = None
         for i in range(count):
             y = run_step(cfg, env.signal, env.gpu, xs[i % nbuf], taps, outs_buf[i % nbuf])
+            if i < len(marks):
+                marks[i].record()
         e1.record()
         torch.cuda.synchronize()
         sampler.sample()
         clocks = sampler.result()
+        prev, per = e0, []
+        for mk in marks:
+            per.append(prev.elapsed_time(mk))
+            prev = mk
+        step_stats["median"], step_stats["max"], step_stats["min"] = float(np.median(per)), float(max(per)), float(min(per))
         return (e0.elapsed_time(e1) / count, clocks, ctx.launch_count() - l0, ctx.get_option("toeplitz_launches") - tc0,
                 ctx.get_option("fixup_launches") - fx0, y, (count - 1) % nbuf, ctx.get_option("os_launches") - os0)
 
@@ -372,7 +391,8 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
         clocks["first_attempt"] = {k: first.get(k) for k in ("sm_mhz", "reasons")}
         remeasured = True
     env.barrier()
-    ms_max = env.max_over_ranks(ms)
+    ms_ranks = env.all_ranks(ms)
+    ms_max = max(ms_ranks)
     value = outs * env.world / (ms_max * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (events on the launching stream) ------------------------------------
@@ -443,7 +463,9 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
                                 "beat the FP32 roofline" if tensor_path else "direct-form FFMA kernel"}
     roofline["shape_roofline"] = {"t_ms": t_roof * 1e3, "gsamples": outs / t_roof / 1e9, "frac": (t_roof * 1e3) / ms,
                                   "note": "BASELINE.md per-shape roofline: max(bytes/measured HBM, 2*K flops/nominal FP32)"}
-    rec = {"workload": cfg["desc"], "rows_per_gpu": rows, "steps": steps, "ms_per_step": ms_max, "value": value, "unit": UNIT,
+    rec = {"workload": cfg["desc"], "rows_per_gpu": rows, "steps": steps, "ms_per_step": ms_max, "ms_by_rank": ms_ranks,
+           "step_ms_rank0": dict(step_stats),
+           "value": value, "unit": UNIT,
            "roofline": roofline, "clocks": clocks, "clock_remeasured": remeasured,
            "gpu_launches": int(launches), "tensor_core_launches": int(tc_launches), "fft_launches": int(os_launches),
            "arithmetic": ("f32 in/out; " + tensor["split"]) if tensor else
@@ -714,6 +736,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="only the headline config (skip `configs` and `strong`)")
+    ap.add_argument("--strong-div", type=int, default=0,
+                    help="debug: run the strong-split phase with rows/D per GPU even at N=1 (what one rank of a D-GPU run does)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="ctx option for A/B runs, e.g. long_tap_path=2 toeplitz_terms=3")
@@ -745,9 +769,9 @@ def main():
 
     want_e2e = not args.no_e2e and cfg["op"] != "ew"
     head, kept = measure_config(env, name, cfg, rows, args.steps, args.warmup, keep=want_e2e)
-    e2e = measure_e2e(env, cfg, rows, args.steps, kept) if want_e2e else None
-    del kept
-    torch.cuda.empty_cache()
+    # (the e2e leg allocates and frees 16 GiB of pinned / pageable host memory and, at N > 1, opens contexts on every GPU
+    # from rank 0: it runs LAST, after every device-resident measurement -- measured: run first, it left a one-off ~110 ms
+    # stall in a later timed region)
 
     # ---- every BASELINE config, same rules (device-resident) --------------------------------------------------
     sweep, strong = None, None
@@ -765,24 +789,30 @@ def main():
             except Exception as e:
                 sweep[cn] = {"error": repr(e)}
         # ---- the BASELINE shapes as FIXED problems split over N GPUs (strong scaling) ------------------------------
-        if world > 1:
+        div = world if world > 1 else args.strong_div
+        if div > 1:
             strong = {}
             for cn in STRONG_CONFIGS:
                 c = CONFIGS[cn]
-                if c["rows"] % world:
+                if c["rows"] % div:
                     continue
                 try:
-                    rec, _ = measure_config(env, cn, c, c["rows"] // world, args.steps, args.warmup)
+                    rec, _ = measure_config(env, cn, c, c["rows"] // div, args.steps, args.warmup)
                     t1 = sweep[cn]["ms_per_step"]                               # the whole problem on ONE GPU, this run (max over ranks)
                     outs_total, _, _ = algorithmic(c, c["rows"])
-                    strong[cn] = {"workload": c["desc"] + f" split over {world} GPUs", "rows_per_gpu": c["rows"] // world,
+                    strong[cn] = {"workload": c["desc"] + f" split over {div} GPUs", "rows_per_gpu": c["rows"] // div,
                                   "ms": rec["ms_per_step"], "value": outs_total / (rec["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
                                   "one_gpu_ms": t1, "speedup_vs_n1": t1 / rec["ms_per_step"],
-                                  "efficiency_vs_n1": t1 / rec["ms_per_step"] / world,
+                                  "efficiency_vs_n1": t1 / rec["ms_per_step"] / div,
                                   "roofline": {k: rec["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")},
+                                  "ms_by_rank": rec["ms_by_rank"], "step_ms_rank0": rec["step_ms_rank0"],
                                   "clocks": rec["clocks"], "parity": rec.get("parity"), "gpu_launches": rec["gpu_launches"]}
                 except Exception as e:
                     strong[cn] = {"error": repr(e)}
+
+    e2e = measure_e2e(env, cfg, rows, args.steps, kept) if want_e2e else None
+    del kept
+    torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None
