@@ -586,20 +586,54 @@ def measure_e2e(env, cfg, rows, steps, kept):
     except MemoryError as e:
         e2e["pageable"] = {"error": repr(e)}
 
-    # ---- ceiling: plain pinned copies of a block of the same traffic, every rank at once ------------------------------
+    # ---- ceiling: what plain pinned copies reach on THIS box, every rank at the same time ---------------------------------
+    # 4 x 1 GiB each way per rank on two streams, all ranks released together by a barrier (an unsynchronised ceiling --
+    # ranks in different phases -- overstates what the host delivers when all GPUs pull at once)
     try:
-        h2d, d2h, dup = C.c_double(), C.c_double(), C.c_double()
-        env.barrier()
-        rcc = lib.scir_b200_microbench_pcie(hctx.handle, 1 << 30, 3, C.byref(h2d), C.byref(d2h), C.byref(dup))
-        if rcc == 0:
-            dup_min = env.min_over_ranks(dup.value)
-            dup_sum = env.sum_over_ranks(dup.value)
-            e2e["ceiling"] = {"h2d_alone_gbs": h2d.value, "d2h_alone_gbs": d2h.value, "duplex_each_way_gbs": dup.value,
-                              "duplex_each_way_gbs_min_over_ranks": dup_min, "duplex_each_way_gbs_sum_over_ranks": dup_sum,
-                              "note": "cudaMemcpyAsync of 1 GiB pinned buffers, both directions at once, all ranks concurrently "
-                                      "(rank 0's figures; min / sum over ranks beside them)",
-                              "frac_of_ceiling": (in_bytes / dt / 1e9) / dup_min if dup_min else None}
-            e2e["ceiling_gbs"] = dup_min
+        nbytes, reps = 1 << 30, 4
+        hp_in = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+        hp_out = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+        hp_in.fill_(1.0)
+        d_in = torch.empty(nbytes // 4, dtype=torch.float32, device=env.dev)
+        d_out = torch.ones(nbytes // 4, dtype=torch.float32, device=env.dev)
+        s1, s2 = torch.cuda.Stream(device=env.dev), torch.cuda.Stream(device=env.dev)
+
+        def copies(h2d, d2h):
+            env.barrier()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            if h2d:
+                with torch.cuda.stream(s1):
+                    ev[0].record()
+                    for _ in range(reps):
+                        d_in.copy_(hp_in, non_blocking=True)
+                    ev[1].record()
+            if d2h:
+                with torch.cuda.stream(s2):
+                    ev[2].record()
+                    for _ in range(reps):
+                        hp_out.copy_(d_out, non_blocking=True)
+                    ev[3].record()
+            torch.cuda.synchronize()
+            t_h = ev[0].elapsed_time(ev[1]) * 1e-3 if h2d else None
+            t_d = ev[2].elapsed_time(ev[3]) * 1e-3 if d2h else None
+            return (reps * nbytes / t_h / 1e9 if h2d else None), (reps * nbytes / t_d / 1e9 if d2h else None)
+
+        copies(True, True)                                                   # warm-up
+        h_alone, _ = copies(True, False)
+        _, d_alone = copies(False, True)
+        h_dup, d_dup = copies(True, True)
+        each = min(h_dup, d_dup)
+        e2e["ceiling"] = {"h2d_alone_gbs": h_alone, "d2h_alone_gbs": d_alone, "duplex_h2d_gbs": h_dup, "duplex_d2h_gbs": d_dup,
+                          "duplex_each_way_gbs_min_over_ranks": env.min_over_ranks(each),
+                          "duplex_each_way_gbs_sum_over_ranks": env.sum_over_ranks(each),
+                          "h2d_alone_gbs_sum_over_ranks": env.sum_over_ranks(h_alone),
+                          "d2h_alone_gbs_sum_over_ranks": env.sum_over_ranks(d_alone),
+                          "note": "4 x 1 GiB pinned copies each way per rank on two streams, every rank released by the same barrier "
+                                  "(rank 0's figures; min / sum over ranks beside them)"}
+        agg = e2e["ceiling"]["duplex_each_way_gbs_sum_over_ranks"]
+        e2e["ceiling"]["frac_of_ceiling"] = (in_bytes * env.world / dt / 1e9) / agg if agg else None
+        e2e["ceiling_gbs"] = agg
+        del hp_in, hp_out, d_in, d_out
     except Exception as e:
         e2e["ceiling"] = {"error": repr(e)}
 

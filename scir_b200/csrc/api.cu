@@ -691,6 +691,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "filtfilt_fused")) return &o.filtfilt_fused;
     if (!strcmp(key, "toeplitz_min_k")) return &o.toeplitz_min_k;
     if (!strcmp(key, "os_min_k")) return &o.os_min_k;
+    if (!strcmp(key, "os_packed")) return &o.os_packed;
     if (!strcmp(key, "toeplitz_min_k_full")) return &o.toeplitz_min_k_full;
     if (!strcmp(key, "toeplitz_loader")) return &o.toeplitz_loader;
     if (!strcmp(key, "host_stage")) return &o.host_stage;

@@ -326,6 +326,278 @@ __global__ void __launch_bounds__(OsGeom<LOGN>::THREADS, OsGeom<LOGN>::MIN_CTAS)
     }
 }
 
+// =====================================================================================================================
+// N = 16384, packed: the same transform with TWO butterflies per thread riding in the two lanes of the packed FP32
+// instructions (FADD2 / FMUL2 / FFMA2: 64 lane-operations per issue slot).  The scalar kernel above is issue-bound
+// (ncu, config 3: 4.2 G warp instructions, 64 % of them FP32 arithmetic, issue slots 63 % busy at one CTA per SM); here
+// every complex add is 2 instructions for two butterflies instead of 4, every complex multiply 4-5 instead of 8.  For
+// that the block lives in shared memory as two PLANES (re[], im[]) and a thread owns the butterflies of two adjacent
+// positions i, i+1: one LDS.64 / STS.64 fetches the same element of both -- already in packed form, no lane shuffles.
+// Pass structure, index arithmetic, twiddles and the spectrum's order are exactly those of fir_os_kernel<14>.
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b)
+{
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+struct C2 {                       // two complex numbers: (re.lo + i im.lo) and (re.hi + i im.hi)
+    u64 re, im;
+};
+__device__ __forceinline__ C2 c2add(C2 a, C2 b) { return C2{add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ C2 c2sub(C2 a, C2 b) { return C2{sub2(a.re, b.re), sub2(a.im, b.im)}; }
+__device__ __forceinline__ C2 c2mul(C2 a, C2 w)               // per-lane complex product a * w
+{
+    return C2{sub2(mul2(a.re, w.re), mul2(a.im, w.im)), fma2(a.re, w.im, mul2(a.im, w.re))};
+}
+__device__ __forceinline__ C2 c2mulc(C2 a, C2 w)              // a * conj(w)
+{
+    return C2{fma2(a.im, w.im, mul2(a.re, w.re)), sub2(mul2(a.im, w.re), mul2(a.re, w.im))};
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft2x(C2 (&a)[R])
+{
+    if constexpr (R == 2) {
+        const C2 t = a[0];
+        a[0] = c2add(t, a[1]);
+        a[1] = c2sub(t, a[1]);
+    } else {
+        C2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) {
+            e[j] = a[2 * j];
+            o[j] = a[2 * j + 1];
+        }
+        dft2x<R / 2, INV>(e);
+        dft2x<R / 2, INV>(o);
+#pragma unroll
+        for (int kk = 0; kk < R / 2; ++kk) {
+            if (kk == 0) {
+                a[0] = c2add(e[0], o[0]);
+                a[R / 2] = c2sub(e[0], o[0]);
+            } else if (kk * 4 == R) {
+                // t = -i o (forward) = (o.im, -o.re);  +i o (inverse) = (-o.im, o.re): folded into the add / sub pattern
+                if (!INV) {
+                    a[kk] = C2{add2(e[kk].re, o[kk].im), sub2(e[kk].im, o[kk].re)};
+                    a[kk + R / 2] = C2{sub2(e[kk].re, o[kk].im), add2(e[kk].im, o[kk].re)};
+                } else {
+                    a[kk] = C2{sub2(e[kk].re, o[kk].im), add2(e[kk].im, o[kk].re)};
+                    a[kk + R / 2] = C2{add2(e[kk].re, o[kk].im), sub2(e[kk].im, o[kk].re)};
+                }
+            } else {
+                const float c = kC16[kk * (16 / R)], sn = kS16[kk * (16 / R)];
+                const u64 cc = pk(c, c), ps = pk(sn, sn), ns = pk(-sn, -sn);
+                // forward w = c - i s: t.re = o.re c + o.im s, t.im = o.im c - o.re s;  inverse w = c + i s
+                const C2 t = INV ? C2{fma2(o[kk].im, ns, mul2(o[kk].re, cc)), fma2(o[kk].re, ps, mul2(o[kk].im, cc))}
+                                 : C2{fma2(o[kk].im, ps, mul2(o[kk].re, cc)), fma2(o[kk].re, ns, mul2(o[kk].im, cc))};
+                a[kk] = c2add(e[kk], t);
+                a[kk + R / 2] = c2sub(e[kk], t);
+            }
+        }
+    }
+}
+
+// a[k] *= w^k (forward) or conj(w^k) (inverse); w holds the two lanes' own twiddles
+template <bool INV>
+__device__ __forceinline__ void twiddle2x(C2 (&a)[16], C2 w1)
+{
+    C2 w[16];
+    w[1] = w1;
+    a[1] = INV ? c2mulc(a[1], w1) : c2mul(a[1], w1);
+#pragma unroll
+    for (int kk = 2; kk < 16; ++kk) {
+        const int hi = os_hibit(kk);
+        w[kk] = (kk == hi) ? c2mul(w[kk / 2], w[kk / 2]) : c2mul(w[hi], w[kk - hi]);
+        a[kk] = INV ? c2mulc(a[kk], w[kk]) : c2mul(a[kk], w[kk]);
+    }
+}
+
+constexpr int kP14N = 16384;
+constexpr int kP14Threads = 512;                           // one butterfly PAIR per thread per radix-16 pass
+__device__ __forceinline__ int ppad(int i) { return i + ((i >> 6) << 2); }          // 4 pad floats per 64: see fir_os.cu notes
+constexpr int kP14Plane = kP14N + (kP14N >> 6) * 4;       // floats per plane
+constexpr size_t kP14Smem = 2 * static_cast<size_t>(kP14Plane) * sizeof(float);
+
+__device__ __forceinline__ C2 tw_pair(const float2* __restrict__ tw, int i0, int i1)
+{
+    const float2 t0 = __ldg(tw + i0), t1 = __ldg(tw + i1);
+    return C2{pk(t0.x, t1.x), pk(t0.y, t1.y)};
+}
+
+template <int LOGNP, bool INV>
+__device__ __forceinline__ void pass16_2x(float* sre, float* sim, const float2* __restrict__ tw, int u)
+{
+    constexpr int logm = LOGNP - 4, m = 1 << logm;
+    const int q = 2 * u;                                   // butterflies q, q + 1: adjacent positions of the same sub-transform
+    const int i = q & (m - 1), base = ((q >> logm) << LOGNP) + i;
+    const C2 w1 = tw_pair(tw, i << (14 - LOGNP), (i + 1) << (14 - LOGNP));
+    C2 a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int pi = ppad(base + (j << logm));
+        a[j].re = *reinterpret_cast<const u64*>(sre + pi);
+        a[j].im = *reinterpret_cast<const u64*>(sim + pi);
+    }
+    if (!INV) {
+        dft2x<16, false>(a);
+        twiddle2x<false>(a, w1);
+    } else {
+        twiddle2x<true>(a, w1);
+        dft2x<16, true>(a);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int pi = ppad(base + (j << logm));
+        *reinterpret_cast<u64*>(sre + pi) = a[j].re;
+        *reinterpret_cast<u64*>(sim + pi) = a[j].im;
+    }
+}
+
+__global__ void __launch_bounds__(kP14Threads, 1) fir_os14_packed_kernel(const __grid_constant__ OsParams q)
+{
+    extern __shared__ __align__(16) float s_pl[];
+    float* const sre = s_pl;
+    float* const sim = s_pl + kP14Plane;
+    constexpr int N = kP14N;
+    const FirPass& p = q.p;
+    const int u = threadIdx.x;
+    const long long pair = blockIdx.x;
+    const long long row = pair / q.pairs_per_row;
+    const long long pr = pair - row * q.pairs_per_row;
+    const long long i0 = p.out_begin + pr * 2 * q.L;
+    const int sgn = (p.dir > 0) ? 1 : -1;
+    const long long a0 = (p.dir > 0) ? i0 - (q.k - 1) : i0 + q.L + (q.k - 1) - 1;
+    const float* __restrict__ xr = p.x + row * p.ld_x;
+    const float2* __restrict__ tw = q.tw;
+    const long long v_lo = (p.dir > 0) ? a0 : a0 - (N - 1), v_hi = (p.dir > 0) ? a0 + q.L + N - 1 : a0 + q.L;
+    const bool interior = q.fast_ok && v_lo >= 0 && v_hi < p.n_v && v_lo + p.in_off >= 0 && v_hi + p.in_off < p.n_x;
+
+    // ---- pass 0 (sub-transform length N, m = 1024) straight from global memory; lanes = positions 2u, 2u + 1 ----
+    int bad;
+    {
+        constexpr int logm = 10;
+        const int i = 2 * u;
+        C2 a[16];
+        if (interior) {
+            const float* __restrict__ xa = xr + (a0 + p.in_off) + sgn * i;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float* e = xa + sgn * (j << logm);
+                a[j].re = pk(__ldg(e), __ldg(e + sgn));
+                a[j].im = pk(__ldg(e + q.L), __ldg(e + q.L + sgn));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const long long ia = a0 + sgn * static_cast<long long>(i + (j << logm));
+                a[j].re = pk(os_vload(p, xr, ia), os_vload(p, xr, ia + sgn));
+                a[j].im = pk(os_vload(p, xr, ia + q.L), os_vload(p, xr, ia + q.L + sgn));
+            }
+        }
+        u64 chk = 0ull;                                    // NaN in either lane iff any sample is NaN / Inf
+#pragma unroll
+        for (int j = 0; j < 16; ++j) chk = fma2(a[j].re, 0ull, fma2(a[j].im, 0ull, chk));
+        float c0, c1;
+        upk(chk, c0, c1);
+        bad = (c0 != c0) | (c1 != c1);
+        dft2x<16, false>(a);
+        twiddle2x<false>(a, tw_pair(tw, i, i + 1));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int pi = ppad(i + (j << logm));
+            *reinterpret_cast<u64*>(sre + pi) = a[j].re;
+            *reinterpret_cast<u64*>(sim + pi) = a[j].im;
+        }
+    }
+    const int any_bad = __syncthreads_or(bad);
+    if (u == 0) q.flags[pair] = any_bad;
+
+    pass16_2x<10, false>(sre, sim, tw, u);
+    __syncthreads();
+    pass16_2x<6, false>(sre, sim, tw, u);
+    __syncthreads();
+    // ---- innermost step: radix-4 forward, times the spectrum, radix-4 inverse (scalar; 4 contiguous positions) ----
+    for (int b4 = u; b4 < N / 4; b4 += kP14Threads) {
+        const int pi = ppad(4 * b4);
+        const float4 r4 = *reinterpret_cast<const float4*>(sre + pi), i4 = *reinterpret_cast<const float4*>(sim + pi);
+        float2 a[4] = {make_float2(r4.x, i4.x), make_float2(r4.y, i4.y), make_float2(r4.z, i4.z), make_float2(r4.w, i4.w)};
+        dft<4, false>(a);
+        const float4 h01 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * b4));
+        const float4 h23 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * b4) + 1);
+        a[0] = cmul(a[0], make_float2(h01.x, h01.y));
+        a[1] = cmul(a[1], make_float2(h01.z, h01.w));
+        a[2] = cmul(a[2], make_float2(h23.x, h23.y));
+        a[3] = cmul(a[3], make_float2(h23.z, h23.w));
+        dft<4, true>(a);
+        *reinterpret_cast<float4*>(sre + pi) = make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
+        *reinterpret_cast<float4*>(sim + pi) = make_float4(a[0].y, a[1].y, a[2].y, a[3].y);
+    }
+    __syncthreads();
+    pass16_2x<6, true>(sre, sim, tw, u);
+    __syncthreads();
+    pass16_2x<10, true>(sre, sim, tw, u);
+    __syncthreads();
+
+    // ---- last inverse pass straight to global memory ----
+    {
+        constexpr int logm = 10;
+        const int i = 2 * u;
+        float* __restrict__ yr = p.y + row * p.ld_y + p.out_off;
+        C2 a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int pi = ppad(i + (j << logm));
+            a[j].re = *reinterpret_cast<const u64*>(sre + pi);
+            a[j].im = *reinterpret_cast<const u64*>(sim + pi);
+        }
+        twiddle2x<true>(a, tw_pair(tw, i, i + 1));
+        dft2x<16, true>(a);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float ra, rb, ia_, ib;
+            upk(a[j].re, ra, rb);
+            upk(a[j].im, ia_, ib);
+#pragma unroll
+            for (int lane = 0; lane < 2; ++lane) {
+                const int n = i + lane + (j << logm);
+                if (n >= q.k - 1) {
+                    const long long o = a0 + sgn * static_cast<long long>(n);
+                    if (o < p.out_end) yr[o] = lane ? rb : ra;
+                    if (o + q.L < p.out_end) yr[o + q.L] = lane ? ib : ia_;
+                }
+            }
+        }
+    }
+}
+
 // Blocks that held a NaN / Inf sample, recomputed like the reference loop (lib.rs:1138-1150): one FMA chain per output.
 __global__ void __launch_bounds__(256) os_fixup_kernel(const __grid_constant__ OsParams q)
 {
@@ -405,13 +677,16 @@ int launch_fir_os(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64
     using SpecKern = void (*)(const float*, int, const float2*, float2*);
     using FirKern = void (*)(const OsParams);
     const SpecKern spec = (logn == 12) ? os_spectrum_kernel<12> : os_spectrum_kernel<14>;
-    const FirKern kern = (logn == 12) ? fir_os_kernel<12> : fir_os_kernel<14>;
-    const size_t smem = (logn == 12) ? OsGeom<12>::SMEM : OsGeom<14>::SMEM;
-    const int threads = (logn == 12) ? OsGeom<12>::THREADS : OsGeom<14>::THREADS;
-    static thread_local bool configured[16][2] = {};
-    const int d = ctx->device & 15, li = (logn == 12) ? 0 : 1;
+    const bool packed = (logn == 14) && ctx->opt.os_packed != 0;            // two butterflies per thread in FADD2 / FFMA2 lanes
+    const FirKern kern = (logn == 12) ? fir_os_kernel<12> : packed ? fir_os14_packed_kernel : fir_os_kernel<14>;
+    const size_t spec_smem = (logn == 12) ? OsGeom<12>::SMEM : OsGeom<14>::SMEM;
+    const size_t smem = packed ? kP14Smem : spec_smem;
+    const int spec_threads = (logn == 12) ? OsGeom<12>::THREADS : OsGeom<14>::THREADS;
+    const int threads = packed ? kP14Threads : spec_threads;
+    static thread_local bool configured[16][3] = {};
+    const int d = ctx->device & 15, li = (logn == 12) ? 0 : packed ? 2 : 1;
     if (!configured[d][li]) {
-        SCIR_CUDA(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "cudaFuncSetAttribute(os_spectrum_kernel)");
+        SCIR_CUDA(cudaFuncSetAttribute(spec, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(spec_smem)), "cudaFuncSetAttribute(os_spectrum_kernel)");
         SCIR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "cudaFuncSetAttribute(fir_os_kernel)");
         configured[d][li] = true;
     }
@@ -423,7 +698,7 @@ int launch_fir_os(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64
         SCIR_CUDA(cudaMemcpyAsync(ctx->os_taps.ptr, ctx->os_taps_host.data(), static_cast<size_t>(k) * sizeof(float), cudaMemcpyHostToDevice,
                                   ctx->stream),
                   "cudaMemcpyAsync(overlap-save taps)");
-        spec<<<1, threads, smem, ctx->stream>>>(static_cast<const float*>(ctx->os_taps.ptr), static_cast<int>(k),
+        spec<<<1, spec_threads, spec_smem, ctx->stream>>>(static_cast<const float*>(ctx->os_taps.ptr), static_cast<int>(k),
                                                  static_cast<const float2*>(ctx->os_tw.ptr), static_cast<float2*>(ctx->os_H.ptr));
         SCIR_CUDA(cudaGetLastError(), "os_spectrum_kernel launch");
         ctx->launches++;
