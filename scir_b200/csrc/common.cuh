@@ -57,7 +57,9 @@ struct Options {
     int64_t variant = 0;        // 0 auto; 1 force generic (non-bulk) tile IO; 2 naive 1-thread/output
     int64_t host_block_rows = 0; // rows per block in the *_host streaming paths (0 = auto)
     int64_t long_tap_path = 0;  // 0 auto (see launch_fir); 1 force FP32 direct; 2 force tcgen05 Toeplitz; 3 force overlap-save FFT
-    int64_t os_packed = 1;      // overlap-save, N = 16384: 1 packed-lane kernel (two butterflies per thread in FADD2/FFMA2), 0 scalar kernel (A/B)
+    int64_t os_packed = 0;      // overlap-save, N = 16384: 1 packed-lane kernel (two butterflies per thread in FADD2/FMUL2/FFMA2: 31 % fewer
+                                // instructions, same 5.9 ms on config 3 -- the kernel is latency / barrier bound at one CTA per SM, not
+                                // issue bound; profiles/README.md), 0 scalar kernel (default)
     int64_t os_min_k = 768;     // auto mode: tap counts from here on take the overlap-save FFT path (large launches).  Measured
                                 // cross-over against the tensor kernel (profiles/README.md): K = 509 6.5 ms tensor vs 9.2 ms FFT
                                 // (config 5), K = 4097 17.0 ms tensor vs 5.8 ms FFT (config 3); the models meet at K ~ 760

@@ -452,13 +452,22 @@ __device__ __forceinline__ C2 tw_pair(const float2* __restrict__ tw, int i0, int
     return C2{pk(t0.x, t1.x), pk(t0.y, t1.y)};
 }
 
+// the two lanes' twiddles W_np^i, W_np^(i+1) of a pass; fetched by the caller BEFORE the barrier that precedes the pass, so
+// the L2 round trip (the 128 KB table does not stay in L1 next to 139 KB of shared memory) hides behind the barrier wait
+template <int LOGNP>
+__device__ __forceinline__ C2 pass_twiddle(const float2* __restrict__ tw, int u)
+{
+    constexpr int m = 1 << (LOGNP - 4);
+    const int i = (2 * u) & (m - 1);
+    return tw_pair(tw, i << (14 - LOGNP), (i + 1) << (14 - LOGNP));
+}
+
 template <int LOGNP, bool INV>
-__device__ __forceinline__ void pass16_2x(float* sre, float* sim, const float2* __restrict__ tw, int u)
+__device__ __forceinline__ void pass16_2x(float* sre, float* sim, const C2 w1, int u)
 {
     constexpr int logm = LOGNP - 4, m = 1 << logm;
     const int q = 2 * u;                                   // butterflies q, q + 1: adjacent positions of the same sub-transform
     const int i = q & (m - 1), base = ((q >> logm) << LOGNP) + i;
-    const C2 w1 = tw_pair(tw, i << (14 - LOGNP), (i + 1) << (14 - LOGNP));
     C2 a[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -537,33 +546,45 @@ __global__ void __launch_bounds__(kP14Threads, 1) fir_os14_packed_kernel(const _
             *reinterpret_cast<u64*>(sim + pi) = a[j].im;
         }
     }
+    C2 wn = pass_twiddle<10>(tw, u);
     const int any_bad = __syncthreads_or(bad);
     if (u == 0) q.flags[pair] = any_bad;
 
-    pass16_2x<10, false>(sre, sim, tw, u);
+    pass16_2x<10, false>(sre, sim, wn, u);
+    wn = pass_twiddle<6>(tw, u);
     __syncthreads();
-    pass16_2x<6, false>(sre, sim, tw, u);
+    pass16_2x<6, false>(sre, sim, wn, u);
+    // the spectrum of the first innermost butterfly is requested before the barrier, each next one a trip ahead
+    float4 h01 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * u));
+    float4 h23 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * u) + 1);
     __syncthreads();
     // ---- innermost step: radix-4 forward, times the spectrum, radix-4 inverse (scalar; 4 contiguous positions) ----
+#pragma unroll 2
     for (int b4 = u; b4 < N / 4; b4 += kP14Threads) {
         const int pi = ppad(4 * b4);
         const float4 r4 = *reinterpret_cast<const float4*>(sre + pi), i4 = *reinterpret_cast<const float4*>(sim + pi);
         float2 a[4] = {make_float2(r4.x, i4.x), make_float2(r4.y, i4.y), make_float2(r4.z, i4.z), make_float2(r4.w, i4.w)};
         dft<4, false>(a);
-        const float4 h01 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * b4));
-        const float4 h23 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * b4) + 1);
-        a[0] = cmul(a[0], make_float2(h01.x, h01.y));
-        a[1] = cmul(a[1], make_float2(h01.z, h01.w));
-        a[2] = cmul(a[2], make_float2(h23.x, h23.y));
-        a[3] = cmul(a[3], make_float2(h23.z, h23.w));
+        const float4 c01 = h01, c23 = h23;
+        if (b4 + kP14Threads < N / 4) {
+            h01 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * (b4 + kP14Threads)));
+            h23 = __ldg(reinterpret_cast<const float4*>(q.H + 4 * (b4 + kP14Threads)) + 1);
+        }
+        a[0] = cmul(a[0], make_float2(c01.x, c01.y));
+        a[1] = cmul(a[1], make_float2(c01.z, c01.w));
+        a[2] = cmul(a[2], make_float2(c23.x, c23.y));
+        a[3] = cmul(a[3], make_float2(c23.z, c23.w));
         dft<4, true>(a);
         *reinterpret_cast<float4*>(sre + pi) = make_float4(a[0].x, a[1].x, a[2].x, a[3].x);
         *reinterpret_cast<float4*>(sim + pi) = make_float4(a[0].y, a[1].y, a[2].y, a[3].y);
     }
+    wn = pass_twiddle<6>(tw, u);
     __syncthreads();
-    pass16_2x<6, true>(sre, sim, tw, u);
+    pass16_2x<6, true>(sre, sim, wn, u);
+    wn = pass_twiddle<10>(tw, u);
     __syncthreads();
-    pass16_2x<10, true>(sre, sim, tw, u);
+    pass16_2x<10, true>(sre, sim, wn, u);
+    wn = tw_pair(tw, 2 * u, 2 * u + 1);
     __syncthreads();
 
     // ---- last inverse pass straight to global memory ----
@@ -578,7 +599,7 @@ __global__ void __launch_bounds__(kP14Threads, 1) fir_os14_packed_kernel(const _
             a[j].re = *reinterpret_cast<const u64*>(sre + pi);
             a[j].im = *reinterpret_cast<const u64*>(sim + pi);
         }
-        twiddle2x<true>(a, tw_pair(tw, i, i + 1));
+        twiddle2x<true>(a, wn);
         dft2x<16, true>(a);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -18,9 +18,10 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def os_ctx():
+def os_ctx(packed=0):
     ctx = gpu.Context(0)
     ctx.set_option("long_tap_path", 3)
+    ctx.set_option("os_packed", packed)        # N = 16384 blocks: 0 scalar kernel (default), 1 packed-lane kernel (A/B arm)
     return ctx
 
 
@@ -39,11 +40,12 @@ def test_os_fir_vs_oracle(batch, n, k):
     x = (rng.rand(batch, n).astype(np.float32) * 2 - 1)
     taps = rng.randn(k).astype(np.float32)
     want = O.fir1d_batched_f32_acc64(x, taps)
-    ctx = os_ctx()
-    y = run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=ctx)).cpu().numpy()
-    assert ctx.get_option("os_launches") == 1                    # the FFT kernel is the one that ran
-    err = np.abs(y - want).max()
-    assert err <= tol(taps, x), (err / tol(taps, x), "of tolerance")
+    for packed in ((0, 1) if k > 640 else (0,)):
+        ctx = os_ctx(packed)
+        y = run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=ctx)).cpu().numpy()
+        assert ctx.get_option("os_launches") == 1                # the FFT kernel is the one that ran
+        err = np.abs(y - want).max()
+        assert err <= tol(taps, x), (packed, err / tol(taps, x), "of tolerance")
 
 
 @pytest.mark.parametrize("k,cutoff", [(255, 0.2), (509, 0.2), (1025, 0.05), (4097, 0.01)])
@@ -59,11 +61,12 @@ def test_os_firwin_margin(k, cutoff):
                     ("tone", (0.9 * np.sin(2 * np.pi * 0.003 * t)).astype(np.float32)[None, :]),
                     ("tone+noise", (0.9 * np.sin(2 * np.pi * 0.003 * t) + 1e-3 * rng.randn(n)).astype(np.float32)[None, :])):
         want = O.lfilter_fir(b, x)
-        ctx = os_ctx()
-        y = run(ctx, lambda: signal.lfilter(b, [1.0], dev(x), ctx=ctx)).cpu().numpy()
-        assert ctx.get_option("os_launches") == 1
-        frac = float(np.abs(y - want).max()) / tol(b, x)
-        assert frac <= 0.25, (k, name, frac, "of tolerance")
+        for packed in ((0, 1) if k > 640 else (0,)):
+            ctx = os_ctx(packed)
+            y = run(ctx, lambda: signal.lfilter(b, [1.0], dev(x), ctx=ctx)).cpu().numpy()
+            assert ctx.get_option("os_launches") == 1
+            frac = float(np.abs(y - want).max()) / tol(b, x)
+            assert frac <= 0.25, (k, name, packed, frac, "of tolerance")
 
 
 def test_os_views_offsets_and_many_blocks():
@@ -102,8 +105,8 @@ def test_os_filtfilt_both_directions(padtype):
     assert_filtfilt_close(yz, O.filtfilt_fir_nopad(b, x), b, x, "zero_state")
 
 
-@pytest.mark.parametrize("k", [63, 300, 2000])
-def test_os_non_finite_samples_stay_local(k):
+@pytest.mark.parametrize("k,packed", [(63, 0), (300, 0), (2000, 0), (2000, 1)])
+def test_os_non_finite_samples_stay_local(k, packed):
     """A NaN / Inf sample must reach exactly the outputs whose window contains it, not its whole FFT block:
     flagged block pairs are redone by os_fixup_kernel the reference's way."""
     rng = np.random.RandomState(k)
@@ -113,7 +116,7 @@ def test_os_non_finite_samples_stay_local(k):
     for r, lst in bad.items():
         for pos, v in lst:
             x[r, pos] = v
-    ctx = os_ctx()
+    ctx = os_ctx(packed)
     y = run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(x), taps, ctx=ctx)).cpu().numpy()
     with np.errstate(invalid="ignore"):
         ref = O.fir1d_batched_f32(x, taps)
