@@ -881,7 +881,9 @@ def main():
 TRAFFIC_PER_LAUNCH = {
     "c2": 8.576e9,      # profiles/r01_c2_fir_toeplitz_kernel_final.ncu.txt: 4.314 GB read + 4.262 GB written (algorithmic 8.590e9)
     "c3": 8.543e9,      # profiles/r01_c3_fir_toeplitz_kernel_final.ncu.txt: 4.297 + 4.246           (algorithmic 8.590e9)
-    "c4": 21.450e9,     # profiles/r01_c4_upfirdn_stream_kernel_ffma2.ncu.txt: 8.612 + 12.838        (algorithmic 21.475e9)
+    "c3_os": 8.547e9,   # profiles/r02_c3_fir_os_kernel.ncu.txt (overlap-save FFT, the default): 4.297 + 4.250
+    "c5_os": 17.140e9,  # profiles/r02_c5_fir_os_kernel_n4096.ncu.txt (A/B arm): 8.592 + 8.548
+    "c4": 21.452e9,     # profiles/r02_c4_upfirdn_ws_kernel.ncu.txt: 8.618 + 12.834                  (algorithmic 21.475e9)
     "c5": 17.169e9,     # profiles/r01_c5_fir_toeplitz_kernel_fused.ncu.txt (one fused pass): 8.599 + 8.570 (algorithmic 17.180e9)
 }
 
