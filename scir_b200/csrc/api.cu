@@ -166,19 +166,24 @@ static int check_taps(const float* taps, int64_t k)
 // K >= toeplitz_min_k (1024) always takes the tensor path, where the direct kernel is 7x slower at any size
 // that matters.  The direct kernel's own streaming floor (~5.2 TB/s) means large launches go to the tensor
 // path even for short filters: there it is simply the better streaming kernel.
-static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t tiles, bool aligned)
+// the tensor kernel's cost: max(20 us, 16 us + rounds * max(3.6 us [HBM share of one tile per SM], 58 ns per MMA))
+static double toeplitz_seconds(const scir_b200_ctx* ctx, int64_t k, int64_t tiles)
 {
-    // fitted to tools/sweep_dispatch.py on B200 (45 shapes, K = 48 .. 511, 64 .. 16384 tiles; profiles/README.md):
-    //   direct:   14 us + per 16384 outputs max(25 ns [its streaming floor, ~5.2 TB/s], (2K + 29) flop / 72 TFLOP/s)
-    //   toeplitz: max(20 us, 16 us + rounds * max(3.6 us [HBM share of one tile per SM], 58 ns per MMA))
-    const double units = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch) / 16384.0;
-    const double t_direct = 14e-6 + units * std::max(25e-9, 16384.0 * (2.0 * static_cast<double>(k) + 29.0) / 72e12);
     const int64_t pmax = (k - 1 + 127) / 128;
     int64_t ksteps = 0;
     for (int64_t pb = 0; pb <= pmax; ++pb) ksteps += 8 - (std::max<int64_t>(0, 128 * pb - (k - 1)) >> 4);
     const double t_round = std::max(3.6e-6, static_cast<double>(3 * ksteps) * 58e-9);
     const double rounds = std::ceil(static_cast<double>(tiles) / static_cast<double>(ctx->sm_count));
-    const double t_toep = std::max(20e-6, 16e-6 + rounds * t_round);
+    return std::max(20e-6, 16e-6 + rounds * t_round);
+}
+
+static bool prefer_toeplitz(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, int64_t tiles, bool aligned)
+{
+    // fitted to tools/sweep_dispatch.py on B200 (45 shapes, K = 48 .. 511, 64 .. 16384 tiles; profiles/README.md):
+    //   direct:   14 us + per 16384 outputs max(25 ns [its streaming floor, ~5.2 TB/s], (2K + 29) flop / 72 TFLOP/s)
+    const double units = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch) / 16384.0;
+    const double t_direct = 14e-6 + units * std::max(25e-9, 16384.0 * (2.0 * static_cast<double>(k) + 29.0) / 72e12);
+    const double t_toep = toeplitz_seconds(ctx, k, tiles);
     // rows that are not 16-byte aligned (odd views / pitches) lose the bulk-copy staging in both families: measured
     // (tools/time_unaligned.py, 256 x 2^18) x1.7 on the tensor kernel, x1.0-1.4 on the direct kernel
     return aligned ? (t_toep < t_direct) : (1.7 * t_toep < 1.2 * t_direct);
@@ -190,9 +195,14 @@ int launch_fir(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t 
     // Long filters: block-FFT convolution (fir_os.cu) does O(log N) work per output where direct form does O(K).
     // Measured cross-over against the tensor kernel: profiles/README.md.  A launch must fill the machine with block
     // pairs (2 (N - K + 1) outputs each) for the FFT path to pay.
-    if ((mode == 3 || (mode == 0 && ctx->opt.variant == 0 && k >= ctx->opt.os_min_k)) && fir_os_supported(ctx, pass, k)) {
-        const double outs = static_cast<double>(pass.out_end - pass.out_begin) * static_cast<double>(pass.batch);
-        if (mode == 3 || outs >= 4.0e6) return launch_fir_os(ctx, pass, c, k);
+    double t_os = 0.0;
+    if ((mode == 3 || (mode == 0 && ctx->opt.variant == 0 && k >= ctx->opt.os_min_k)) && fir_os_supported(ctx, pass, k, &t_os)) {
+        if (mode == 3) return launch_fir_os(ctx, pass, c, k);
+        int64_t tiles = 0;
+        bool aligned = false;
+        // against the tensor kernel's model (the FFT path reads rows with scalar loads: alignment does not matter to it)
+        if (!toeplitz_supported(ctx, pass, k, &tiles, &aligned) || t_os < (aligned ? 1.0 : 1.7) * toeplitz_seconds(ctx, k, tiles))
+            return launch_fir_os(ctx, pass, c, k);
     }
     if (mode != 1 && mode != 3 && ctx->opt.variant == 0) {
         int64_t tiles = 0;

@@ -60,9 +60,10 @@ struct Options {
     int64_t os_packed = 0;      // overlap-save, N = 16384: 1 packed-lane kernel (two butterflies per thread in FADD2/FMUL2/FFMA2: 31 % fewer
                                 // instructions, same 5.9 ms on config 3 -- the kernel is latency / barrier bound at one CTA per SM, not
                                 // issue bound; profiles/README.md), 0 scalar kernel (default)
-    int64_t os_min_k = 768;     // auto mode: tap counts from here on take the overlap-save FFT path (large launches).  Measured
-                                // cross-over against the tensor kernel (profiles/README.md): K = 509 6.5 ms tensor vs 9.2 ms FFT
-                                // (config 5), K = 4097 17.0 ms tensor vs 5.8 ms FFT (config 3); the models meet at K ~ 760
+    int64_t os_min_k = 512;     // auto mode: from this tap count on the overlap-save FFT path is COSTED against the tensor kernel
+                                // (api.cu: launch_fir) and taken when cheaper.  Measured (profiles/README.md): K = 509 6.5 ms tensor
+                                // vs 9.2 ms FFT (config 5), K = 4097 17.0 ms tensor vs 5.8 ms FFT (config 3); the models meet at
+                                // K ~ 760 for long rows, later for rows shorter than a block pair
     int64_t toeplitz_terms = 3; // split products per tap: 3 (hh,hm,mh), 4 (+mm), 6 (+hl,lh)
     int64_t toeplitz_split = 0; // operand format of the split: 0 block-scaled FP16 (11-bit terms), 1 BF16 (8-bit terms)
     int64_t toeplitz_chains = 1; // accumulation chains per tile in TMEM (2: consecutive MMAs alternate accumulators; measured: no gain)
@@ -200,7 +201,7 @@ bool toeplitz_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k
 int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 
 // ---- long-tap overlap-save path (FP32 shared-memory FFT, fir_os.cu) -------------------------------------------
-bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k);
+bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, double* est_seconds = nullptr);
 int launch_fir_os(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k);
 
 int64_t upfirdn_out_len(int64_t len_h, int64_t in_len, int64_t up, int64_t down);

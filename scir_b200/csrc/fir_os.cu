@@ -660,7 +660,7 @@ int os_logn_for(int64_t k)
 
 }  // namespace
 
-bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k)
+bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k, double* est_seconds)
 {
     if (k < 2 || k > SCIR_B200_MAX_TAPS) return false;
     if (pass.batch <= 0 || pass.out_end <= pass.out_begin) return false;
@@ -670,7 +670,17 @@ bool fir_os_supported(const scir_b200_ctx* ctx, const FirPass& pass, int64_t k)
     if (OsGeom<14>::SMEM > static_cast<size_t>(ctx->max_smem_optin)) return false;
     const long long blocks = (pass.out_end - pass.out_begin + L - 1) / L;
     const long long pairs = (blocks + 1) / 2;
-    return pairs * pass.batch <= 0x7fffffffLL;
+    if (pairs * pass.batch > 0x7fffffffLL) return false;
+    if (est_seconds) {
+        // measured per block pair and SM (profiles/README.md): N = 16384, one CTA per SM: 19.9 us (config 3: 5.81 ms for 295.8
+        // pairs per SM); N = 4096, three CTAs per SM, 13.5 us each (config 5 arm: 9.24 ms for 2048 pairs per SM).  A row shorter than
+        // a pair still pays for the whole pair, which is what keeps short rows off this path.
+        const double t_cta = (logn == 14) ? 19.9e-6 : 13.5e-6;
+        const double resident = (logn == 14) ? 1.0 : 3.0;
+        const double per_sm = std::ceil(static_cast<double>(pairs * pass.batch) / static_cast<double>(ctx->sm_count));
+        *est_seconds = 12e-6 + std::ceil(per_sm / resident) * t_cta;
+    }
+    return true;
 }
 
 int launch_fir_os(scir_b200_ctx* ctx, const FirPass& pass, const float* c, int64_t k)

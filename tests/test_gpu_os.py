@@ -150,17 +150,24 @@ def test_os_dynamic_range_error_model():
     assert err[0, 40000:].max() <= tol(b, x[1])               # quiet blocks of the loud row, away from the burst
 
 
-def test_auto_dispatch_uses_fft_path_for_long_taps_and_large_launches():
+def test_auto_dispatch_costs_the_fft_path_against_the_tensor_kernel():
+    """api.cu: launch_fir takes the FFT path when its cost model beats the tensor kernel's: long filters on rows that fill
+    block pairs (config 3's shape) -- not short filters, not the 509 fused taps of config 5, not rows much shorter than a
+    block pair (which would pay for whole 16384-point transforms)."""
     rng = np.random.RandomState(5)
     ctx = gpu.Context(0)
-    small = dev(rng.rand(2, 50000).astype(np.float32))
-    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(small, rng.randn(2000).astype(np.float32), ctx=ctx))
-    assert ctx.get_option("os_launches") == 0                 # too small to fill the machine with block pairs
     big = dev(rng.rand(64, 1 << 17).astype(np.float32))
-    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(big, rng.randn(2000).astype(np.float32), ctx=ctx))
-    assert ctx.get_option("os_launches") == 1
+    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(big, rng.randn(4097).astype(np.float32), ctx=ctx))
+    assert ctx.get_option("os_launches") == 1                 # long taps, long rows: FFT
     run(ctx, lambda: gpu.fir1d_batched_f32_cuda(big, rng.randn(63).astype(np.float32), ctx=ctx))
-    assert ctx.get_option("os_launches") == 1                 # short filters stay on the tensor / direct kernels
+    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(big, rng.randn(509).astype(np.float32), ctx=ctx))
+    assert ctx.get_option("os_launches") == 1                 # short and mid-length filters stay on the tensor / direct kernels
+    short_rows = dev(rng.rand(4096, 5000).astype(np.float32))
+    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(short_rows, rng.randn(1025).astype(np.float32), ctx=ctx))
+    assert ctx.get_option("os_launches") == 1                 # a 5000-sample row would pay for a whole 16384-point pair
     ctx.set_option("long_tap_path", 2)
-    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(big, rng.randn(2000).astype(np.float32), ctx=ctx))
+    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(big, rng.randn(4097).astype(np.float32), ctx=ctx))
     assert ctx.get_option("os_launches") == 1 and ctx.get_option("toeplitz_launches") >= 1
+    ctx.set_option("long_tap_path", 3)
+    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(short_rows, rng.randn(1025).astype(np.float32), ctx=ctx))
+    assert ctx.get_option("os_launches") == 2                 # forced

@@ -275,6 +275,7 @@ def test_auto_dispatch_uses_tensor_path_for_long_taps():
     rng = np.random.RandomState(5)
     x = dev(rng.rand(2, 50000).astype(np.float32))
     ctx = gpu.Context(0)
+    ctx.set_option("os_min_k", 1 << 20)                    # this test is about direct vs tensor: keep the FFT path out of it
     run(ctx, lambda: gpu.fir1d_batched_f32_cuda(x, rng.randn(63).astype(np.float32), ctx=ctx))
     assert ctx.get_option("toeplitz_launches") == 0
     run(ctx, lambda: gpu.fir1d_batched_f32_cuda(x, rng.randn(2000).astype(np.float32), ctx=ctx))

@@ -70,7 +70,9 @@ print('$spec ->', round(d['ms_per_step'],4), 'ms', round(d['value'],1), 'Gs/s', 
 fi
 if has launches; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
-     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-sweep > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_all_configs.csv \
+     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launches_all.log 2>&1; echo "ncu launches (all configs) rc=$?"
 fi
 for cfg in c2 c4 c5 c3; do
   if has ncu_$cfg; then
