@@ -43,3 +43,14 @@ def test_cpp_mirror_on_gpu():
     _build()
     res = subprocess.run([EXE, "gpu"], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
+
+
+def test_copy_pool_host_staging_logic():
+    """The pinned-ring staging of the *_host entry points is plain host code (scir_b200/csrc/copy_pool.hpp): streaming copies
+    at every alignment and strided 2-D submissions over a thread pool, tested here without a GPU."""
+    exe = os.path.join(ROOT, "build", "copy_pool_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "copy_pool_test.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", src, "-o", exe], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
