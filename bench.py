@@ -414,6 +414,14 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
             else:
                 passes = 2
         per_out, mma_per_tile = executed_mma_flops_per_out(k, terms)
+        hh_blocks = 0
+        try:                                                # what the last launch really issued (small-tap blocks run hi x hi only)
+            mpt = ctx.get_option("toeplitz_mma_per_tile")
+            hh_blocks = ctx.get_option("toeplitz_hh_blocks")
+            if mpt > 0:
+                per_out, mma_per_tile = per_out * mpt / mma_per_tile, mpt
+        except Exception:
+            pass
         exec_tf = outs * passes * per_out / (ms * 1e-3) / 1e12
         tc_peak = float(env.peaks.get("bf16_tflops", 2250.0))
         t_tensor = outs * passes * per_out / (tc_peak * 1e12)
@@ -424,7 +432,7 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
                   "peak_sustained_tflops": env.peaks.get("bf16_tflops_sustained"),
                   "frac_executed": exec_tf / tc_peak,
                   "algorithmic_tflops": achieved_tf, "frac_algorithmic_x_terms": achieved_tf * terms / tc_peak,
-                  "mma_per_tile": mma_per_tile}
+                  "mma_per_tile": mma_per_tile, "blocks_hi_x_hi_only": hh_blocks}
         if t_tensor > t_hbm:
             bound = "tensor"
     traffic = TRAFFIC_PER_LAUNCH.get(name) if rows == CONFIGS[name]["rows"] else None

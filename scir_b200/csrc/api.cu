@@ -694,6 +694,7 @@ static int64_t* option_slot(Options& o, const char* key)
     if (!strcmp(key, "toeplitz_split")) return &o.toeplitz_split;
     if (!strcmp(key, "toeplitz_chains")) return &o.toeplitz_chains;
     if (!strcmp(key, "toeplitz_ts")) return &o.toeplitz_ts;
+    if (!strcmp(key, "toeplitz_adaptive_budget")) return &o.toeplitz_adaptive_budget;
     if (!strcmp(key, "toeplitz_stcs")) return &o.toeplitz_stcs;
     if (!strcmp(key, "toeplitz_tn")) return &o.toeplitz_tn;
     if (!strcmp(key, "toeplitz_tn_short")) return &o.toeplitz_tn_short;
@@ -726,6 +727,14 @@ int scir_b200_ctx_get_option(const scir_b200_ctx* ctx, const char* key, int64_t*
     if (!value) return set_error(SCIR_B200_ERR_INVALID_ARG, "value is NULL");
     if (key && !strcmp(key, "toeplitz_launches")) {                   // read-only statistic
         *value = static_cast<int64_t>(ctx->toeplitz_launches);
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "toeplitz_mma_per_tile")) {            // read-only statistic (last Toeplitz launch)
+        *value = ctx->toeplitz_last_mma_per_tile;
+        return SCIR_B200_OK;
+    }
+    if (key && !strcmp(key, "toeplitz_hh_blocks")) {               // read-only statistic (last Toeplitz launch)
+        *value = ctx->toeplitz_last_hh_blocks;
         return SCIR_B200_OK;
     }
     if (key && !strcmp(key, "os_launches")) {                      // read-only statistic

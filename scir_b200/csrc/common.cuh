@@ -72,6 +72,8 @@ struct Options {
     int64_t toeplitz_tn = 0;     // tile width of the Toeplitz kernel: 0 auto, 64 or 128 columns
     int64_t toeplitz_tn_short = 128; // auto: width for filters with K <= 129 (64 = deeper prefetch; measured in profiles/README.md)
     int64_t toeplitz_stcs = 0;   // 1: evict-first hint on the epilogue's output stores (A/B)
+    int64_t toeplitz_adaptive_budget = 500; // tensor kernel: thousandths of the tolerance 1e-5 * sum|c| * max|x| that dropping the two mid-term
+                                 // products of small-tap Toeplitz blocks may cost in the worst case (fir_toeplitz.cu: make_plan); 0 = never drop
     int64_t toeplitz_ts = 1;     // 1: keep the first Toeplitz blocks in TMEM (A operand from TMEM); 0: all operands from shared memory
     int64_t toeplitz_loader = 0; // 0 auto (TMA-fed in-place buffers when they fit); 1 force the register-prefetch loader
     int64_t toeplitz_min_k = 1024; // auto mode: tap counts from here on always take the tensor path
@@ -104,6 +106,8 @@ struct scir_b200_ctx {
     int max_smem_optin = 0;
     uint64_t launches = 0;
     uint64_t toeplitz_launches = 0;        // launches served by the tcgen05 Toeplitz kernel
+    int toeplitz_last_mma_per_tile = 0;    // MMAs per tile of the last Toeplitz launch, and how many of its blocks ran hi x hi only
+    int toeplitz_last_hh_blocks = 0;
     uint64_t filtfilt_fused_calls = 0;     // filtfilt calls served by the single-pass form
     uint64_t fixup_launches = 0;           // non-finite fix-up kernels (one after every FIR launch; idle on finite data)
     uint64_t poly_launches = 0;            // launches served by the polyphase TILE kernel (tests)

@@ -80,6 +80,7 @@ struct ToepParams {
     int slab_cols;                      // odd, >= TN + pmax
     int nver;                           // split terms kept per operand: 2 (hi, mid) or 3 (+ lo)
     int terms;                          // 3, 4 or 6 products
+    int mma_per_tile;                   // MMAs issued per 128 x tn tile (statistic)
     int mode;                           // MODE_REGISTER / MODE_INPLACE
     int nbuf;                           // slab buffers: 3 in place, 1 or 2 in register mode
     int fmt;                            // FMT_F16_SCALED / FMT_BF16
@@ -96,6 +97,8 @@ struct ToepParams {
                                         // changes): keeps the launch parameters at ~300 B -- 32 KB of by-value taps made the
                                         // two launches of a pass cost 30-60 us of host time
     int stream_stores;                  // 1: epilogue stores carry the evict-first hint (st.global.cs): outputs are written once
+    unsigned long long hh_mask;         // bit pb set: Toeplitz block pb multiplies hi x hi only (its taps are so small that the two
+                                        // mid-term products stay inside the error budget: make_plan, "precision per block")
 };
 
 // ---- tcgen05 / TMEM PTX ----------------------------------------------------------------------------------
@@ -298,20 +301,23 @@ __device__ __forceinline__ void issue_tile(const ToepParams& q, bool leader, uin
         const int ks0 = max(0, TB * pb - (q.k - 1)) >> 4;                // first K step with a non-zero tap in T_p
         uint32_t a = a_lo0 + 8u * static_cast<uint32_t>(16 * (q.pmax - pb) + 2 * ks0);
         uint32_t x = x_lo0 + static_cast<uint32_t>(ks0) * two_cols + static_cast<uint32_t>(q.pmax - pb);
+        const bool full = !((q.hh_mask >> pb) & 1ull);                    // (only ever cleared for TERMS == 3)
         if (pb < q.ts_blocks) {
             uint32_t at = a_tmem0 + static_cast<uint32_t>(pb) * NVER * 64u + static_cast<uint32_t>(ks0) * 8u;
             for (int ks = ks0; ks < TB / 16; ++ks) {
                 if (leader) {
                     mma_ts(at, x);                                       // hi * hi
-                    mma_ts(at, x + ver16);                               // hi * mid
-                    mma_ts(at + 64u, x);                                 // mid * hi
+                    if (full) {
+                        mma_ts(at, x + ver16);                           // hi * mid
+                        mma_ts(at + 64u, x);                             // mid * hi
+                    }
                     if constexpr (TERMS >= 4) mma_ts(at + 64u, x + ver16);
                     if constexpr (TERMS == 6) {
                         mma_ts(at, x + 2u * ver16);                      // hi * lo
                         mma_ts(at + 128u, x);                            // lo * hi
                     }
                 } else {
-                    idx += TERMS;
+                    idx += full ? TERMS : TERMS - 2;
                 }
                 at += 8u;
                 x += two_cols;
@@ -320,15 +326,17 @@ __device__ __forceinline__ void issue_tile(const ToepParams& q, bool leader, uin
             for (int ks = ks0; ks < TB / 16; ++ks) {
                 if (leader) {
                     mma(a, x);                                           // hi * hi
-                    mma(a, x + ver16);                                   // hi * mid
-                    mma(a + hank16, x);                                  // mid * hi
+                    if (full) {
+                        mma(a, x + ver16);                               // hi * mid
+                        mma(a + hank16, x);                              // mid * hi
+                    }
                     if constexpr (TERMS >= 4) mma(a + hank16, x + ver16);
                     if constexpr (TERMS == 6) {
                         mma(a, x + 2u * ver16);                          // hi * lo
                         mma(a + 2u * hank16, x);                         // lo * hi
                     }
                 } else {
-                    idx += TERMS;
+                    idx += full ? TERMS : TERMS - 2;
                 }
                 a += 16u;
                 x += two_cols;
@@ -813,6 +821,44 @@ bool make_plan(const scir_b200_ctx* ctx, const FirPass& pass, const float* c, in
             q.tap_inv = std::ldexp(1.f, -se);
         }
     }
+    // ---- precision per Toeplitz block ------------------------------------------------------------------------------
+    // Block pb holds the taps c[128 pb - 127 .. 128 pb + 127].  Dropping its two mid-term products (c_h x_m + c_m x_h)
+    // costs at most 2 * 2^-11 * S_pb * max|x| per output, S_pb = sum of |c| over those taps (|x_m| <= 2^-11 |x| and
+    // |c_m| <= 2^-11 |c|: FP16 keeps 11 significant bits).  Windowed-sinc designs put almost all of sum|c| in one or two
+    // blocks: the others are multiplied hi x hi only, as long as the dropped terms of ALL such blocks together stay
+    // within `toeplitz_adaptive_budget` thousandths of the path's tolerance 1e-5 * sum|c| * max|x| (default 0.5; the
+    // always-dropped mid x mid products, the operands' third terms and FP32 accumulation use another ~0.15-0.2 in the worst
+    // case).  Config 5's fused 509-tap pass: the two outer of its 5 blocks hold 0.45 % of sum|c|: 120 -> 88 MMAs per tile.  Random or flat taps: nothing is dropped.  0 disables.
+    q.hh_mask = 0ull;
+    q.mma_per_tile = 0;
+    {
+        std::vector<std::pair<double, int>> blocks;
+        double total = 0.0;
+        if (c != nullptr)
+            for (int64_t i = 0; i < k; ++i) total += std::fabs(static_cast<double>(c[i]));
+        if (c != nullptr && q.fmt == FMT_F16_SCALED && q.terms == 3 && ctx->opt.toeplitz_adaptive_budget > 0 && total > 0.0 &&
+            std::isfinite(total) && q.pmax < 64) {
+            for (int pb = 0; pb <= q.pmax; ++pb) {
+                const int64_t lo = std::max<int64_t>(0, static_cast<int64_t>(TB) * pb - (TB - 1));
+                const int64_t hi = std::min<int64_t>(k - 1, static_cast<int64_t>(TB) * pb + (TB - 1));
+                double sb = 0.0;
+                for (int64_t i = lo; i <= hi; ++i) sb += std::fabs(static_cast<double>(c[i]));
+                blocks.emplace_back(sb, pb);
+            }
+            std::sort(blocks.begin(), blocks.end());
+            const double budget = static_cast<double>(ctx->opt.toeplitz_adaptive_budget) * 1e-3 * 1e-5 * total / (2.0 * 4.8828125e-4);
+            double used = 0.0;
+            for (const auto& b : blocks) {
+                if (used + b.first > budget) break;
+                used += b.first;
+                q.hh_mask |= 1ull << b.second;
+            }
+        }
+        for (int pb = 0; pb <= q.pmax; ++pb) {
+            const int ks0 = std::max(0, TB * pb - (q.k - 1)) >> 4;
+            q.mma_per_tile += (TB / 16 - ks0) * (((q.hh_mask >> pb) & 1ull) ? q.terms - 2 : q.terms);
+        }
+    }
     // outputs wanted, in causal index space i'
     q.ip_lo = (pass.dir > 0) ? pass.out_begin : (pass.n_v - pass.out_end);
     q.ip_hi = (pass.dir > 0) ? pass.out_end : (pass.n_v - pass.out_begin);
@@ -892,6 +938,8 @@ int launch_fir_toeplitz(scir_b200_ctx* ctx, const FirPass& pass, const float* c,
     ctx->launches += 2;                                    // the contraction and its (normally idle) fix-up
     ctx->fixup_launches++;
     ctx->toeplitz_launches++;
+    ctx->toeplitz_last_mma_per_tile = plan.q.mma_per_tile;
+    ctx->toeplitz_last_hh_blocks = __builtin_popcountll(plan.q.hh_mask);
     return SCIR_B200_OK;
 }
 

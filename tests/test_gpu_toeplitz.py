@@ -103,6 +103,42 @@ def test_toeplitz_high_dynamic_range_error_model():
     assert np.abs(yd[0, quiet] - want[0, quiet]).max() <= tol(b, x[1])
 
 
+@pytest.mark.parametrize("loader", [0, 1])
+def test_toeplitz_precision_per_block_stays_inside_the_budget(loader):
+    """Toeplitz blocks whose taps are tiny run hi x hi only (fir_toeplitz.cu: make_plan).  The rule is a worst-case bound --
+    dropped terms of all such blocks <= 0.5 of the tolerance -- so it must hold on inputs that make every dropped product
+    pull the same way: constants, the worst FP16/BF16 rounding value, +-1 patterns following the taps' signs.  Config 5's
+    zero-phase filter (b (*) flip(b), 509 taps) is the shape it exists for; flat / random taps must drop nothing."""
+    from scipy.signal import firwin
+    rng = np.random.RandomState(77)
+    b = firwin(255, 0.2).astype(np.float64)
+    hc = np.convolve(b, b[::-1]).astype(np.float32)
+    n = 1 << 16
+    worst = np.float32(1.0 + 2.0 ** -11 + 2.0 ** -22)               # rounds DOWN in fp16: x_m has the sign of x everywhere
+    signs = np.sign(hc[::-1]).astype(np.float32)
+    signs[signs == 0] = 1
+    cases = {"uniform": (rng.rand(2, n).astype(np.float32) * 2 - 1), "const": np.full((1, n), 0.7, np.float32),
+             "worst_fp16": np.full((1, n), worst, np.float32),
+             "tap_signs": (np.tile(signs, n // hc.size + 1)[:n] * worst)[None, :].astype(np.float32)}
+    fracs = {}
+    for name, x in cases.items():
+        want = O.lfilter_fir(hc, x)
+        for budget in (500, 0):
+            ctx = toep_ctx(3, loader, 0)
+            ctx.set_option("toeplitz_adaptive_budget", budget)
+            y = run(ctx, lambda: signal.lfilter(hc, [1.0], dev(x), ctx=ctx)).cpu().numpy()
+            nhh, mpt = ctx.get_option("toeplitz_hh_blocks"), ctx.get_option("toeplitz_mma_per_tile")
+            assert (nhh, mpt) == ((2, 88) if budget else (0, 120)), (budget, nhh, mpt)
+            fracs[(name, budget)] = float(np.abs(y - want).max()) / tol(hc, x)
+            assert fracs[(name, budget)] <= 0.8, (name, budget, fracs[(name, budget)])
+    print({k: round(v, 3) for k, v in fracs.items()})
+    # taps without small blocks: nothing may be dropped
+    ctx = toep_ctx(3, loader, 0)
+    flat = rng.randn(509).astype(np.float32)
+    run(ctx, lambda: gpu.fir1d_batched_f32_cuda(dev(cases["uniform"]), flat, ctx=ctx))
+    assert ctx.get_option("toeplitz_hh_blocks") == 0 and ctx.get_option("toeplitz_mma_per_tile") == 120
+
+
 def test_toeplitz_error_budget_reported():
     """How much of the 1e-5 tolerance each split uses on BASELINE-shaped data (firwin taps, U[-1,1)), on a
     coherent case (constant input, mostly positive taps) and on the value that is worst for a two-term BF16
