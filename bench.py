@@ -287,7 +287,10 @@ class Env:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # every collective of this script is tiny and follows at most a few seconds of rank-local work: a rank that
+            # waits for minutes is a bug, and a fast abort beats a 10-minute watchdog hang
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
         self.opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
         self.variant = args.variant
         self.hbm_peak, self.peak_src, self.peaks = measured_peaks()
@@ -297,6 +300,12 @@ class Env:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def any_rank(self, flag) -> bool:
+        """True on EVERY rank if `flag` is true on any rank.  Every decision that changes how many collectives a rank
+        goes on to call (re-measuring, skipping a leg after a failed allocation) must go through this: a rank-local
+        branch around a barrier deadlocks the job (it did: one GPU's clock sample re-measured alone at N = 8)."""
+        return self.max_over_ranks(1.0 if flag else 0.0) > 0.0
 
     def max_over_ranks(self, v):
         t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
@@ -384,7 +393,7 @@ def measure_config(env, name, cfg, rows, steps, warmup, want_parity=True, keep=F
     env.barrier()
     ms, clocks, launches, tc_launches, fx_launches, y, last, os_launches = timed(steps)
     remeasured = False
-    if ClockSampler.rejected(clocks):                       # the contract: rejected once, measured again
+    if env.any_rank(ClockSampler.rejected(clocks)):         # the contract: rejected once, measured again -- by ALL ranks together
         env.barrier()
         first = clocks
         ms, clocks, launches, tc_launches, fx_launches, y, last, os_launches = timed(steps)
@@ -569,11 +578,17 @@ def measure_e2e(env, cfg, rows, steps, kept):
         e2e["error"] = L.last_error()
 
     # ---- the same call on PAGEABLE arrays: what a Rust Vec / ndarray::Array2 / numpy array is (lib.rs:1042-1044) ----
+    px = py = None
     try:
         px = np.empty((rows, n), np.float32)
         py = np.empty((rows, n_out), np.float32)
         px[:] = ax
         py[:] = 0
+    except MemoryError:
+        px = py = None
+    if env.any_rank(px is None):
+        e2e["pageable"] = {"error": "pageable test arrays could not be allocated on every rank"}
+    else:
         pin = C.c_int(-1)
         lib.scir_b200_host_is_pinned(px.ctypes.data_as(C.c_void_p), px.nbytes, C.byref(pin))
         _, pcall = host_call(env, cfg, taps, hctx.handle, px.ctypes.data_as(fpp), py.ctypes.data_as(fpp), rows)
@@ -590,20 +605,25 @@ def measure_e2e(env, cfg, rows, steps, kept):
                            "copy_threads": hctx.get_option("host_copy_threads") or "auto"}
         if rcp != 0:
             e2e["pageable"]["error"] = L.last_error()
-        del px, py
-    except MemoryError as e:
-        e2e["pageable"] = {"error": repr(e)}
+    del px, py
 
     # ---- ceiling: what plain pinned copies reach on THIS box, every rank at the same time ---------------------------------
     # 4 x 1 GiB each way per rank on two streams, all ranks released together by a barrier (an unsynchronised ceiling --
     # ranks in different phases -- overstates what the host delivers when all GPUs pull at once)
+    nbytes, reps = 1 << 30, 4
+    hp_in = hp_out = d_in = d_out = None
     try:
-        nbytes, reps = 1 << 30, 4
         hp_in = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
         hp_out = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
         hp_in.fill_(1.0)
         d_in = torch.empty(nbytes // 4, dtype=torch.float32, device=env.dev)
         d_out = torch.ones(nbytes // 4, dtype=torch.float32, device=env.dev)
+    except Exception as e:                                  # rank-local failure: agreed on below, before any collective
+        hp_in = None
+        e2e["ceiling"] = {"error": repr(e)}
+    if env.any_rank(hp_in is None):
+        e2e.setdefault("ceiling", {"error": "pinned buffers for the ceiling test could not be allocated on every rank"})
+    else:
         s1, s2 = torch.cuda.Stream(device=env.dev), torch.cuda.Stream(device=env.dev)
 
         def copies(h2d, d2h):
@@ -641,9 +661,7 @@ def measure_e2e(env, cfg, rows, steps, kept):
         agg = e2e["ceiling"]["duplex_each_way_gbs_sum_over_ranks"]
         e2e["ceiling"]["frac_of_ceiling"] = (in_bytes * env.world / dt / 1e9) / agg if agg else None
         e2e["ceiling_gbs"] = agg
-        del hp_in, hp_out, d_in, d_out
-    except Exception as e:
-        e2e["ceiling"] = {"error": repr(e)}
+    del hp_in, hp_out, d_in, d_out
 
     # ---- N > 1: the in-process front end north_star (d) describes -- rank 0 drives all N GPUs, the others wait ------
     if env.world > 1:
@@ -826,10 +844,9 @@ def main():
             c = CONFIGS[cn]
             outs_c, abytes_c, _ = algorithmic(c, c["rows"])
             steps_c = args.steps if abytes_c > 3e8 else max(args.steps, 200)     # short configs: enough steps for the clock sampler
-            try:
-                sweep[cn], _ = measure_config(env, cn, c, c["rows"], steps_c, args.warmup)
-            except Exception as e:
-                sweep[cn] = {"error": repr(e)}
+            # (no try/except here: measure_config is full of collectives -- a rank that swallowed an exception would leave
+            # the others waiting; an uncaught one aborts the whole job at once)
+            sweep[cn], _ = measure_config(env, cn, c, c["rows"], steps_c, args.warmup)
         # ---- the BASELINE shapes as FIXED problems split over N GPUs (strong scaling) ------------------------------
         div = world if world > 1 else args.strong_div
         if div > 1:
@@ -838,19 +855,16 @@ def main():
                 c = CONFIGS[cn]
                 if c["rows"] % div:
                     continue
-                try:
-                    rec, _ = measure_config(env, cn, c, c["rows"] // div, args.steps, args.warmup)
-                    t1 = sweep[cn]["ms_per_step"]                               # the whole problem on ONE GPU, this run (max over ranks)
-                    outs_total, _, _ = algorithmic(c, c["rows"])
-                    strong[cn] = {"workload": c["desc"] + f" split over {div} GPUs", "rows_per_gpu": c["rows"] // div,
-                                  "ms": rec["ms_per_step"], "value": outs_total / (rec["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
-                                  "one_gpu_ms": t1, "speedup_vs_n1": t1 / rec["ms_per_step"],
-                                  "efficiency_vs_n1": t1 / rec["ms_per_step"] / div,
-                                  "roofline": {k: rec["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")},
-                                  "ms_by_rank": rec["ms_by_rank"], "step_ms_rank0": rec["step_ms_rank0"],
-                                  "clocks": rec["clocks"], "parity": rec.get("parity"), "gpu_launches": rec["gpu_launches"]}
-                except Exception as e:
-                    strong[cn] = {"error": repr(e)}
+                rec, _ = measure_config(env, cn, c, c["rows"] // div, args.steps, args.warmup)   # (collectives inside: no try/except)
+                t1 = sweep[cn]["ms_per_step"]                                   # the whole problem on ONE GPU, this run (max over ranks)
+                outs_total, _, _ = algorithmic(c, c["rows"])
+                strong[cn] = {"workload": c["desc"] + f" split over {div} GPUs", "rows_per_gpu": c["rows"] // div,
+                              "ms": rec["ms_per_step"], "value": outs_total / (rec["ms_per_step"] * 1e-3) / 1e9, "unit": UNIT,
+                              "one_gpu_ms": t1, "speedup_vs_n1": t1 / rec["ms_per_step"],
+                              "efficiency_vs_n1": t1 / rec["ms_per_step"] / div,
+                              "roofline": {k: rec["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms")},
+                              "ms_by_rank": rec["ms_by_rank"], "step_ms_rank0": rec["step_ms_rank0"],
+                              "clocks": rec["clocks"], "parity": rec.get("parity"), "gpu_launches": rec["gpu_launches"]}
 
     e2e = measure_e2e(env, cfg, rows, args.steps, kept) if want_e2e else None
     del kept

@@ -64,3 +64,85 @@ def test_row_sharding_and_gather_world2(batch):
     assert all(ok for _, ok, _ in res)
     blocks = sorted(b for _, _, b in res)
     assert blocks[0][0] == 0 and blocks[-1][1] == batch and blocks[0][1] == blocks[1][0]
+
+
+# ---- bench.py's cross-rank agreement helpers (world_size 2, gloo) ---------------------------------------------------
+# Round 2 lost an 8-GPU run to a rank-local `if rejected(clocks): barrier()`: one GPU's clock sample re-measured alone and
+# the job deadlocked.  Every decision that changes how many collectives a rank calls goes through Env.any_rank now.
+def _agree_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        import bench
+        env = bench.Env.__new__(bench.Env)                  # the helpers only need these attributes (no CUDA here)
+        env.torch, env.dist, env.dev, env.world, env.rank = torch, dist, torch.device("cpu"), world, rank
+        ok = env.any_rank(rank == 1) is True                # true on ONE rank => true on every rank
+        ok = ok and env.any_rank(False) is False
+        ok = ok and env.all_ranks(10.0 + rank) == [10.0, 11.0]
+        ok = ok and env.max_over_ranks(float(rank)) == 1.0 and env.min_over_ranks(float(rank)) == 0.0
+        ok = ok and env.sum_over_ranks(1.5) == 3.0
+        # the control flow of measure_config's re-measure: only rank 1 "sees a bad clock", both ranks take the branch
+        calls = 0
+        if env.any_rank(rank == 1):
+            dist.barrier()
+            calls += 1
+        dist.barrier()
+        ok = ok and calls == 1
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_rank_agreement_helpers_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_agree_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
+
+
+def test_bench_has_no_rank_local_branch_around_a_collective():
+    """Static check of bench.py: inside measure_config / measure_e2e / main, a call to env.barrier() or a cross-rank
+    reduction must not sit under an `if` / `try` whose outcome can differ between ranks.  Allowed guards: conditions built
+    only from run-wide facts (world size, args, config names, `env.any_rank(..)` results)."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    collective = {"barrier", "max_over_ranks", "min_over_ranks", "sum_over_ranks", "all_ranks", "any_rank"}
+    run_wide = ("env.world", "world", "args.", "env.any_rank", "want_e2e", "div", "name in", "cfg[", "c[", "h2d", "d2h", "k > 0",
+                "ok_all", "self.world")
+
+    def has_collective(node):
+        for n in ast.walk(node):
+            if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr in collective:
+                return True
+            if isinstance(n, ast.Call) and isinstance(n.func, ast.Name) and n.func.id in ("timed", "copies", "measure_config"):
+                return True
+        return False
+
+    bad = []
+    for fn in ast.walk(tree):
+        if not isinstance(fn, ast.FunctionDef) or fn.name not in ("measure_config", "measure_e2e", "main"):
+            continue
+        for node in ast.walk(fn):
+            if isinstance(node, ast.If) and has_collective(ast.Module(body=node.body + node.orelse, type_ignores=[])):
+                cond = ast.unparse(node.test)
+                if not any(tok in cond for tok in run_wide):
+                    bad.append((fn.name, node.lineno, cond))
+            if isinstance(node, ast.Try) and has_collective(ast.Module(body=node.body, type_ignores=[])):
+                # a try whose body holds collectives is only safe when the handler cannot swallow a rank-local failure:
+                # the rank-0-only mg leg sits between two barriers all ranks reach regardless
+                src = ast.unparse(node)
+                if "scir_b200_mg_create" not in src:
+                    bad.append((fn.name, node.lineno, "try"))
+    assert not bad, bad
