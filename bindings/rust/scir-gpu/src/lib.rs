@@ -212,6 +212,53 @@ mod cuda {
         Array2::from_shape_vec((b, n), out_host).map_err(|_| GpuError::ShapeMismatch)
     }
 
+    /// The in-process multi-GPU front end (north_star (d)): rows (channels) of one host array sharded over several
+    /// devices, one stream and one host thread per device, no collective (`scir_b200_mg_*`).
+    pub struct MultiGpu {
+        raw: *mut ffi::ScirB200Mg,
+    }
+
+    impl MultiGpu {
+        /// One shard per entry of `devices` (a device may be listed more than once).
+        pub fn new(devices: &[i32]) -> Result<Self, GpuError> {
+            let mut raw = ptr::null_mut();
+            check(unsafe { ffi::scir_b200_mg_create(devices.as_ptr(), devices.len() as i32, &mut raw) })?;
+            Ok(Self { raw })
+        }
+        /// All devices of the box.
+        pub fn all_devices() -> Result<Self, GpuError> {
+            let mut n = 0;
+            check(unsafe { ffi::scir_b200_device_count(&mut n) })?;
+            let devs: Vec<i32> = (0..n).collect();
+            Self::new(&devs)
+        }
+        /// `fir1d_batched_f32` with the rows sharded over the devices; same values as the single-device call.
+        pub fn fir1d_batched_f32(&self, x: &Array2<f32>, taps: &Array1<f32>) -> Result<Array2<f32>, GpuError> {
+            let (b, n) = x.dim();
+            let x_std = x.as_standard_layout();
+            let x_host = x_std.as_slice().ok_or(GpuError::ShapeMismatch)?;
+            let taps_std = taps.as_standard_layout();
+            let taps_host = taps_std.as_slice().ok_or(GpuError::ShapeMismatch)?;
+            let mut out_host = vec![0.0f32; b * n];
+            let ld = if n > 0 { n as i64 } else { 1 };
+            check(unsafe {
+                ffi::scir_b200_mg_fir1d_batched_f32_host(
+                    self.raw, x_host.as_ptr(), ld, taps_host.as_ptr(), taps_host.len() as i64, ffi::SCIR_B200_TAPS_SCIR,
+                    out_host.as_mut_ptr(), ld, b as i64, n as i64,
+                )
+            })?;
+            Array2::from_shape_vec((b, n), out_host).map_err(|_| GpuError::ShapeMismatch)
+        }
+    }
+
+    impl Drop for MultiGpu {
+        fn drop(&mut self) {
+            unsafe {
+                ffi::scir_b200_mg_destroy(self.raw);
+            }
+        }
+    }
+
     /// Device storage of a [`super::DeviceArray<f32>`]: owned by the default ctx of the creating thread.
     pub(crate) struct DeviceBuf {
         pub(crate) ptr: *mut c_void,
@@ -255,7 +302,7 @@ mod cuda {
 }
 
 #[cfg(feature = "cuda")]
-pub use cuda::{fir1d_batched_f32_cuda, with_default_context, Context};
+pub use cuda::{fir1d_batched_f32_cuda, with_default_context, Context, MultiGpu};
 
 /// A shaped array with dtype that lives on the host or -- after `to_device(Device::Cuda)` -- in B200 memory
 /// (`lib.rs:77-190`, where the CUDA arm only re-tagged a host `Vec`).  Device storage is f32 (the FIR path's dtype).

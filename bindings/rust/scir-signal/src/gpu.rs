@@ -160,6 +160,103 @@ mod routes {
         Ok(out)
     }
 
+    fn run_f32(
+        x: &[f32],
+        n_out_total: usize,
+        f: impl FnOnce(&scir_gpu::Context, *const f32, *mut f32) -> std::os::raw::c_int,
+    ) -> Result<Vec<f32>, GpuError> {
+        let mut out = vec![0.0f32; n_out_total];
+        with_default_context(|ctx| {
+            let dx = DevBuf::new(ctx, x.len() * 4)?;
+            let dy = DevBuf::new(ctx, n_out_total * 4)?;
+            let res = (|| {
+                check(unsafe { ffi::scir_b200_memcpy_h2d(ctx.as_ptr(), dx.0, x.as_ptr() as *const _, x.len() * 4) })?;
+                check(f(ctx, dx.0 as *const f32, dy.0 as *mut f32))?;
+                check(unsafe { ffi::scir_b200_memcpy_d2h(ctx.as_ptr(), out.as_mut_ptr() as *mut _, dy.0, n_out_total * 4) })
+            })();
+            unsafe {
+                ffi::scir_b200_free(ctx.as_ptr(), dx.0);
+                ffi::scir_b200_free(ctx.as_ptr(), dy.0);
+            }
+            res
+        })?;
+        Ok(out)
+    }
+
+    /// Signal-extension modes of `upfirdn` / `resample_poly` (SciPy's MODE enum, `_upfirdn_apply.pyx:77-86`).
+    #[derive(Clone, Copy, Debug, PartialEq, Eq)]
+    pub enum ExtMode {
+        /// pad with `cval`
+        Constant,
+        /// d c b a | a b c d | d c b a
+        Symmetric,
+        /// a a a a | a b c d | d d d d
+        Edge,
+        /// linear continuation of the first / last slope
+        Smooth,
+        /// a b c d | a b c d | a b c d
+        Wrap,
+        /// d c b | a b c d | c b a
+        Reflect,
+        /// -d -c -b -a | a b c d | -d -c -b -a
+        Antisymmetric,
+        /// odd reflection about the end samples
+        Antireflect,
+        /// the line through the first and last sample
+        Line,
+    }
+
+    impl ExtMode {
+        fn code(self) -> std::os::raw::c_int {
+            match self {
+                ExtMode::Constant => ffi::SCIR_B200_EXT_CONSTANT,
+                ExtMode::Symmetric => ffi::SCIR_B200_EXT_SYMMETRIC,
+                ExtMode::Edge => ffi::SCIR_B200_EXT_EDGE,
+                ExtMode::Smooth => ffi::SCIR_B200_EXT_SMOOTH,
+                ExtMode::Wrap => ffi::SCIR_B200_EXT_PERIODIC,
+                ExtMode::Reflect => ffi::SCIR_B200_EXT_REFLECT,
+                ExtMode::Antisymmetric => ffi::SCIR_B200_EXT_ANTISYMMETRIC,
+                ExtMode::Antireflect => ffi::SCIR_B200_EXT_ANTIREFLECT,
+                ExtMode::Line => ffi::SCIR_B200_EXT_LINE,
+            }
+        }
+    }
+
+    /// `upfirdn(h, x, up, down, mode, cval)` along the rows (SciPy `_upfirdn.py:107-216`); output is
+    /// `(rows, _output_len(len(h), n, up, down))`.
+    pub fn upfirdn(h: &Array1<f32>, x: &Array2<f32>, up: usize, down: usize, mode: ExtMode, cval: f32) -> Result<Array2<f32>, GpuError> {
+        let (rows, n) = x.dim();
+        let n_out = unsafe { ffi::scir_b200_upfirdn_out_len(h.len() as i64, n as i64, up as i64, down as i64) } as usize;
+        let xs = x.as_standard_layout();
+        let hs = h.as_standard_layout();
+        let out = run_f32(xs.as_slice().ok_or(GpuError::ShapeMismatch)?, rows * n_out, |ctx, dx, dy| unsafe {
+            ffi::scir_b200_upfirdn_mode_f32(
+                ctx.as_ptr(), hs.as_ptr(), hs.len() as i64, up as i64, down as i64, mode.code(), cval, dx, ld(n), rows as i64,
+                n as i64, dy, ld(n_out), 0, n_out as i64,
+            )
+        })?;
+        Array2::from_shape_vec((rows, n_out), out).map_err(|_| GpuError::ShapeMismatch)
+    }
+
+    /// `resample_poly(x, up, down, window=h, padtype=<extension mode>, cval)` (SciPy `_signaltools.py:3921-3957`).
+    pub fn resample_poly_pad(
+        x: &Array2<f32>, up: usize, down: usize, window: &Array1<f32>, padtype: ExtMode, cval: f32,
+    ) -> Result<Array2<f32>, GpuError> {
+        let (rows, n) = x.dim();
+        let mut plan = ffi::ScirB200ResamplePlan::default();
+        check(unsafe { ffi::scir_b200_resample_poly_plan(n as i64, window.len() as i64, up as i64, down as i64, &mut plan) })?;
+        let n_out = if plan.up == 1 && plan.down == 1 { n } else { plan.n_out as usize };
+        let xs = x.as_standard_layout();
+        let ws = window.as_standard_layout();
+        let out = run_f32(xs.as_slice().ok_or(GpuError::ShapeMismatch)?, rows * n_out, |ctx, dx, dy| unsafe {
+            ffi::scir_b200_resample_poly_pad_f32(
+                ctx.as_ptr(), ws.as_ptr(), ws.len() as i64, up as i64, down as i64, padtype.code(), cval, dx, ld(n), rows as i64,
+                n as i64, dy, ld(n_out),
+            )
+        })?;
+        Array2::from_shape_vec((rows, n_out), out).map_err(|_| GpuError::ShapeMismatch)
+    }
+
     /// f64 twin of the reference's `resample_poly(input: &Array1<f64>, up, down)` (sig/lib.rs:313-362) for ANY rate
     /// and filter: SciPy's `resample_poly(x, up, down, window=h)` on one f64 row, computed in f64 on the device.
     pub fn resample_poly_f64(input: &Array1<f64>, up: usize, down: usize, window: &Array1<f64>) -> Result<Array1<f64>, GpuError> {
@@ -192,4 +289,6 @@ mod routes {
 }
 
 #[cfg(feature = "cuda")]
-pub use routes::{filtfilt_fir, filtfilt_fir_f64, lfilter_fir, resample_poly, resample_poly_f64, PadType};
+pub use routes::{
+    filtfilt_fir, filtfilt_fir_f64, lfilter_fir, resample_poly, resample_poly_f64, resample_poly_pad, upfirdn, ExtMode, PadType,
+};
