@@ -307,6 +307,20 @@ class Env:
         branch around a barrier deadlocks the job (it did: one GPU's clock sample re-measured alone at N = 8)."""
         return self.max_over_ranks(1.0 if flag else 0.0) > 0.0
 
+    def guarded(self, fn):
+        """(result, None) or (None, error text) -- the SAME branch on every rank.  A deterministic failure (a bug, an
+        out-of-memory every rank hits) is caught on all ranks at the same point and reported in the JSON line instead of
+        losing the whole run; a failure on one rank alone, in the middle of another rank's collectives, still ends in the
+        process group's 180 s timeout -- an abort, not a hang."""
+        out, err = None, None
+        try:
+            out = fn()
+        except Exception as e:                              # noqa: BLE001 -- reported, not swallowed
+            err = repr(e)
+        if self.any_rank(err is not None):
+            return None, err or "failed on another rank"
+        return out, None
+
     def max_over_ranks(self, v):
         t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
         if self.world > 1:
@@ -844,9 +858,9 @@ def main():
             c = CONFIGS[cn]
             outs_c, abytes_c, _ = algorithmic(c, c["rows"])
             steps_c = args.steps if abytes_c > 3e8 else max(args.steps, 200)     # short configs: enough steps for the clock sampler
-            # (no try/except here: measure_config is full of collectives -- a rank that swallowed an exception would leave
-            # the others waiting; an uncaught one aborts the whole job at once)
-            sweep[cn], _ = measure_config(env, cn, c, c["rows"], steps_c, args.warmup)
+            # (failures are agreed across ranks: Env.guarded)
+            res, err = env.guarded(lambda: measure_config(env, cn, c, c["rows"], steps_c, args.warmup)[0])
+            sweep[cn] = res if err is None else {"error": err}
         # ---- the BASELINE shapes as FIXED problems split over N GPUs (strong scaling) ------------------------------
         div = world if world > 1 else args.strong_div
         if div > 1:
@@ -855,7 +869,10 @@ def main():
                 c = CONFIGS[cn]
                 if c["rows"] % div:
                     continue
-                rec, _ = measure_config(env, cn, c, c["rows"] // div, args.steps, args.warmup)   # (collectives inside: no try/except)
+                rec, err = env.guarded(lambda: measure_config(env, cn, c, c["rows"] // div, args.steps, args.warmup)[0])
+                if err is not None or "ms_per_step" not in sweep.get(cn, {}):
+                    strong[cn] = {"error": err or "the one-GPU measurement of this config failed"}
+                    continue
                 t1 = sweep[cn]["ms_per_step"]                                   # the whole problem on ONE GPU, this run (max over ranks)
                 outs_total, _, _ = algorithmic(c, c["rows"])
                 strong[cn] = {"workload": c["desc"] + f" split over {div} GPUs", "rows_per_gpu": c["rows"] // div,
@@ -866,7 +883,11 @@ def main():
                               "ms_by_rank": rec["ms_by_rank"], "step_ms_rank0": rec["step_ms_rank0"],
                               "clocks": rec["clocks"], "parity": rec.get("parity"), "gpu_launches": rec["gpu_launches"]}
 
-    e2e = measure_e2e(env, cfg, rows, args.steps, kept) if want_e2e else None
+    e2e = None
+    if want_e2e:
+        e2e, err = env.guarded(lambda: measure_e2e(env, cfg, rows, args.steps, kept))
+        if err is not None:
+            e2e = {"value": None, "unit": UNIT, "error": err}
     del kept
     torch.cuda.empty_cache()
 

@@ -92,6 +92,16 @@ def _agree_worker(rank, world, port, q):
             calls += 1
         dist.barrier()
         ok = ok and calls == 1
+        # Env.guarded: a failure every rank hits is reported on every rank; a failure on one rank (after the same
+        # collectives) turns into an error on all of them; success passes the result through
+        def boom():
+            raise RuntimeError("same on every rank")
+        res, err = env.guarded(boom)
+        ok = ok and res is None and "same on every rank" in err
+        res, err = env.guarded(lambda: (_ for _ in ()).throw(ValueError("rank 1 only")) if rank == 1 else 7)
+        ok = ok and res is None and err is not None and (("rank 1 only" in err) == (rank == 1))
+        res, err = env.guarded(lambda: 40 + rank)
+        ok = ok and err is None and res == 40 + rank
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
