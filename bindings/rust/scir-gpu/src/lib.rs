@@ -22,6 +22,7 @@ use ndarray::{Array1, Array2};
 use std::error::Error;
 use std::fmt;
 
+/// Raw `extern "C"` declarations of `libscir_b200.so` (generated from `include/scir_b200.h`).
 #[cfg(feature = "cuda")]
 pub mod ffi;
 
@@ -267,11 +268,11 @@ mod cuda {
 
     impl DeviceBuf {
         pub(crate) fn alloc(len: usize) -> Result<Self, GpuError> {
-            let mut ptr = ptr::null_mut();
+            let mut raw: *mut c_void = ptr::null_mut();
             with_default_context(|ctx| {
-                check(unsafe { ffi::scir_b200_malloc(ctx.as_ptr(), len.max(1) * 4, &mut ptr) })
+                check(unsafe { ffi::scir_b200_malloc(ctx.as_ptr(), len.max(1) * 4, &mut raw) })
             })?;
-            Ok(Self { ptr, len })
+            Ok(Self { ptr: raw, len })
         }
         pub(crate) fn upload(host: &[f32]) -> Result<Self, GpuError> {
             let buf = Self::alloc(host.len())?;
